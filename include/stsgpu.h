@@ -1,0 +1,240 @@
+/*
+ * stsgpu.h - C ABI of the B200-native engine for the per-bitstream test kernels of sts
+ *            (the improved NIST SP800-22 suite, arcetri/sts v3.2.7).
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no C++/torch types.
+ * It replaces, for the hot path only,
+ *
+ *   - the dispatch/batching of src/utils/utilities.c:1479-1884
+ *     (handleFileBasedBitStreams / testBits / parseBitsBinaryInput / copyBitsToEpsilon), and
+ *   - the compute part of the 15 X_iterate() bodies in src/tests/ (*.c) reached through
+ *     iterate() in src/utils/driver.c:395-425,
+ *
+ * while the reference's host driver, plugin table (struct driver, driver.c:55-61), record
+ * keeping tails, .pvalues files and result.txt assessment stay as they are.  INTEGRATION.md shows
+ * the glue a maintainer adds on the reference side.
+ *
+ * Data contract
+ * -------------
+ * Input: `nstreams` bitstreams of `n` bits each, as the RAW FILE BYTES sts reads with -F r:
+ * stream s occupies bytes [s*n/8, (s+1)*n/8); bit k of a stream is
+ * (byte[k/8] >> (7 - k%8)) & 1  (utilities.c:1862-1872, MSB first).  n % 8 == 0 is required,
+ * exactly as parse_args.c:939 requires it.
+ *
+ * Output, per stream (one "record"), in three flat arrays whose per-test offsets are given by
+ * stsgpu_get_layout():
+ *   pvals  (double)   the p-values in exactly the order X_iterate appends them to
+ *                     state->p_val[test] (and therefore the order of the .pvalues file,
+ *                     utilities.c:1967-2024); NON_P_VALUE (-99999999.0, defs.h:314) where the
+ *                     reference records it.
+ *   istats (int64_t)  the integer statistics each test derives from the bits (see STSGPU_ST_*).
+ *   wcount (uint32_t) W[template][block] of the non-overlapping template test,
+ *                     ntemplates x 8, template-major.
+ *
+ * Threading: one context per GPU, single caller per context.  No CPU fallback exists: every entry
+ * point fails with STSGPU_E_CUDA / STSGPU_E_NO_DEVICE when no usable B200 is present.
+ */
+#ifndef STSGPU_H
+#define STSGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STSGPU_ABI_VERSION 1
+
+/* test numbers: identical to enum test, defs.h:217-236 */
+enum {
+	STSGPU_TEST_FREQUENCY = 1,
+	STSGPU_TEST_BLOCK_FREQUENCY = 2,
+	STSGPU_TEST_CUSUM = 3,
+	STSGPU_TEST_RUNS = 4,
+	STSGPU_TEST_LONGEST_RUN = 5,
+	STSGPU_TEST_RANK = 6,
+	STSGPU_TEST_DFT = 7,
+	STSGPU_TEST_NON_OVERLAPPING = 8,
+	STSGPU_TEST_OVERLAPPING = 9,
+	STSGPU_TEST_UNIVERSAL = 10,
+	STSGPU_TEST_APEN = 11,
+	STSGPU_TEST_RND_EXCURSION = 12,
+	STSGPU_TEST_RND_EXCURSION_VAR = 13,
+	STSGPU_TEST_SERIAL = 14,
+	STSGPU_TEST_LINEARCOMPLEXITY = 15,
+	STSGPU_NUMOFTESTS = 15
+};
+#define STSGPU_ALL_TESTS 0xFFFEu	/* bits 1..15 */
+#define STSGPU_NON_P_VALUE (-99999999.0)	/* defs.h:314 */
+
+/* error codes (negative); 0 is success */
+enum {
+	STSGPU_OK = 0,
+	STSGPU_E_INVAL = -1,		/* bad argument */
+	STSGPU_E_NO_DEVICE = -2,	/* no CUDA device / not sm_100 */
+	STSGPU_E_CUDA = -3,		/* a CUDA runtime call or kernel failed */
+	STSGPU_E_NOMEM = -4,		/* host or device allocation failed */
+	STSGPU_E_UNSUPPORTED = -5,	/* parameter combination outside the engine's limits */
+	STSGPU_E_STATE = -6,		/* call sequence error (e.g. wait without submit) */
+	STSGPU_E_NCCL = -7,		/* NCCL missing or failed */
+	STSGPU_E_RANGE = -8		/* iteration / index out of range */
+};
+
+/*
+ * Test parameters: the subset of struct TP (defs.h:277-289) the kernels depend on, plus the
+ * batch geometry.  Field meanings and defaults are the reference's (-P 1..6,9; defs.h:110-125).
+ */
+typedef struct stsgpu_params {
+	int32_t abi_version;		/* must be STSGPU_ABI_VERSION */
+	int32_t device;			/* CUDA device ordinal */
+	int64_t n;			/* tp.n: bits per stream (default 1048576) */
+	int64_t max_streams;		/* capacity of one submit (streams per batch) */
+	uint32_t test_mask;		/* bit t set <=> state->testVector[t] (1..15) */
+	int32_t reserved0;
+	int64_t block_frequency_M;	/* tp.blockFrequencyBlockLength      (16384) */
+	int32_t non_overlapping_m;	/* tp.nonOverlappingTemplateLength   (9) */
+	int32_t overlapping_m;		/* tp.overlappingTemplateLength      (9) */
+	int32_t apen_m;			/* tp.approximateEntropyBlockLength  (10) */
+	int32_t serial_m;		/* tp.serialBlockLength              (16) */
+	int64_t linear_complexity_M;	/* tp.linearComplexitySequenceLength (500) */
+} stsgpu_params;
+
+/* per-stream record layout; offsets are in elements of the respective array */
+typedef struct stsgpu_layout {
+	uint32_t enabled_mask;		/* tests still enabled after the X_init style checks */
+	int32_t npv;			/* p-values per stream */
+	int32_t nst;			/* int64 statistics per stream */
+	int32_t nw;			/* uint32 W counts per stream (= ntemplates * 8) */
+	int32_t ntemplates;		/* non-overlapping templates (148 for m = 9) */
+	int32_t universal_L;		/* L chosen by the rule of universal.c:145-178 */
+	int32_t pv_off[STSGPU_NUMOFTESTS + 1], pv_cnt[STSGPU_NUMOFTESTS + 1];
+	int32_t st_off[STSGPU_NUMOFTESTS + 1], st_cnt[STSGPU_NUMOFTESTS + 1];
+} stsgpu_layout;
+
+/*
+ * istats slots, relative to st_off[test]:
+ *  FREQUENCY        [0] S_n                                          (frequency.c:191-201)
+ *  BLOCK_FREQUENCY  [0] N, [1..N] ones in block i                    (blockFrequency.c:217-237)
+ *  CUSUM            [0] S, [1] S_max, [2] S_min, [3] z_fwd, [4] z_bwd (cusum.c:221-236)
+ *  RUNS             [0] ones, [1] V_n, [2] test_possible             (runs.c:213-240)
+ *  LONGEST_RUN      [0..6] class counts                              (longestRunOfOnes.c:383-409)
+ *  RANK             [0] F_32, [1] F_31, [2] F_remaining              (rank.c:303-327)
+ *  DFT              [0] N_1                                          (discreteFourierTransform.c:407-411)
+ *  NON_OVERLAPPING  none (see wcount)
+ *  OVERLAPPING      [0..5] v[k]                                      (overlappingTemplateMatchings.c:262-296)
+ *  UNIVERSAL        [0] bit pattern of the double `sum`              (universal.c:355-375)
+ *  APEN             [0] bits of phi(m), [1] bits of phi(m+1), [2] sum C_m[i]^2,
+ *                   [3] sum C_{m+1}[i]^2, [4] sum i*C_m[i], [5] sum i*C_{m+1}[i]
+ *                                                                    (approximateEntropy.c:369-407)
+ *  RND_EXCURSION    [0] J, [1 + 8*k + i] v[k][i], k = 0..5, i = 0..7 (randomExcursions.c:324-464)
+ *  RND_EXCURSION_VAR [0] J, [1 + i] xi(state i), i = 0..17           (randomExcursionsVariant.c:262-306)
+ *  SERIAL           [0..2] sum v_i^2 for block sizes m, m-1, m-2     (serial.c:390-419)
+ *  LINEARCOMPLEXITY [0..6] v[class]                                  (linearComplexity.c:367-377)
+ */
+
+typedef struct stsgpu_ctx stsgpu_ctx;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+/* fill *p with the reference's defaults (defs.h:110-125) for n bits, all 15 tests enabled */
+void stsgpu_default_params(stsgpu_params *p);
+
+/*
+ * Create an engine.  Plays the role of the parts of the 15 X_init() that validate parameters
+ * and size per-thread scratch (e.g. blockFrequency.c:102-129, universal.c:145-178,
+ * nonOverlappingTemplateMatchings.c:211-241): tests whose preconditions fail are disabled, as in
+ * the reference, and reported through layout.enabled_mask.
+ */
+int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out);
+void stsgpu_destroy(stsgpu_ctx *ctx);
+int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out);
+
+/* ---- the iterate() replacement ------------------------------------------------------------ */
+
+/*
+ * Submit `nstreams` (<= max_streams) streams of raw file bytes (nstreams * n/8 bytes at `raw`,
+ * borrowed until stsgpu_wait returns).  `first_iteration` is the reference's iteration index of
+ * the first stream (thread_state->iteration_being_done, defs.h:489-494).  Asynchronous: H2D copy,
+ * all enabled test kernels and the D2H copy of the records are queued on the engine's streams.
+ * Replaces parseBitsBinaryInput + copyBitsToEpsilon + iterate() (utilities.c:1601-1625).
+ */
+int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams, int64_t first_iteration);
+
+/*
+ * Same, for input that is already resident in the engine's device input buffer (filled by
+ * stsgpu_generate_lcg or stsgpu_upload): no H2D inside.
+ */
+int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration);
+
+/* copy raw bytes into the device input buffer without running the tests */
+int stsgpu_upload(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams);
+
+/* block until the submitted batch is done and its records are in host memory */
+int stsgpu_wait(stsgpu_ctx *ctx);
+
+/*
+ * Records of the last completed batch: pointers to engine-owned pinned host arrays of
+ * nstreams*npv doubles, nstreams*nst int64 and nstreams*nw uint32, valid until the next submit.
+ */
+int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first_iteration,
+		   const double **pvals, const int64_t **istats, const uint32_t **wcount);
+
+/* ---- synthetic input: tools/generators.c LCG, generator 1 ----------------------- */
+
+/*
+ * Fill the device input buffer with streams [first_stream, first_stream + nstreams) of the
+ * reference's LCG generator output (generators.c:797-905: x <- 950706376 x mod (2^31-1) from
+ * 23482349, bit = x >= 2^30, packed LSB-first by write_sequence), i.e. byte-identical to
+ * `generators 1 <count>` for n = 2^20.  Uses skip-ahead, so any rank can start anywhere.
+ */
+int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_t nstreams);
+
+/* copy the device input buffer back (tests / fixtures) */
+int stsgpu_download_input(stsgpu_ctx *ctx, uint8_t *raw, int64_t nstreams);
+
+/* ---- pinned host memory for the caller's read buffers -------------------------------------- */
+void *stsgpu_host_alloc(size_t bytes);
+void stsgpu_host_free(void *p);
+
+/* ---- multi-GPU: gather records to a root rank over NCCL ------------------------- */
+
+#define STSGPU_UNIQUE_ID_BYTES 128
+/* rank 0 obtains an id and distributes it out of band (file, env, torchrun store ...) */
+int stsgpu_comm_unique_id(uint8_t id[STSGPU_UNIQUE_ID_BYTES]);
+int stsgpu_comm_init(stsgpu_ctx *ctx, const uint8_t id[STSGPU_UNIQUE_ID_BYTES], int rank, int nranks);
+/*
+ * Gather the p-values of the last completed batch of every rank to `root`, rank-major (rank r's
+ * streams follow rank r-1's: the reference's -j job order, utilities.c:1526).  Every rank must
+ * have completed a batch of the same nstreams.  On root, *pvals_all points to
+ * nranks*nstreams*npv doubles in engine-owned pinned memory; elsewhere it is NULL.
+ */
+int stsgpu_gather_pvals(stsgpu_ctx *ctx, int root, const double **pvals_all);
+int stsgpu_comm_barrier(stsgpu_ctx *ctx);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+
+/* enable per-kernel CUDA-event timing of subsequent submits (adds event records only) */
+int stsgpu_set_profiling(stsgpu_ctx *ctx, int on);
+/* kernels launched by the last submit; name/ms for entry i (ms valid after stsgpu_wait) */
+int stsgpu_kernel_count(const stsgpu_ctx *ctx);
+int stsgpu_kernel_info(stsgpu_ctx *ctx, int i, const char **name, float *ms);
+/* device time of the last batch (first kernel start -> records ready to copy), in ms */
+int stsgpu_last_batch_ms(stsgpu_ctx *ctx, float *ms);
+/* total kernel launches issued by this context so far */
+int64_t stsgpu_launch_count(const stsgpu_ctx *ctx);
+
+/* ---- debugging / parity helpers ------------------------------------------------------------ */
+
+/* cyclic pattern histogram at `bits` (<= 21) of stream `s` of the last batch, 2^bits uint32 */
+int stsgpu_debug_pattern_histogram(stsgpu_ctx *ctx, int64_t s, int bits, uint32_t *hist);
+
+const char *stsgpu_strerror(int code);
+/* detail of the last failure on this context (CUDA error string, failing call) */
+const char *stsgpu_last_error(const stsgpu_ctx *ctx);
+int stsgpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif				/* STSGPU_H */
