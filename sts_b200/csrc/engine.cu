@@ -1,0 +1,726 @@
+/*
+ * engine.cu - the C ABI of include/stsgpu.h: context, parameter checks that mirror the X_init()
+ * self-disable rules, device buffers, batch submission and result records.
+ *
+ * HBM layout of one context (n = 2^20, capacity B streams):
+ *   d_in        B x pitch bytes   raw file bytes of every stream, pitch = 128-byte multiple >= n/8 + 16
+ *   d_pv/d_st/d_w                 B records (188 doubles, 176 int64, 1184 uint32 at defaults)
+ *   d_apen_hist B x 3 * 2^apen_m  uint32, the two ApEn histograms in index order
+ *   d_dft_work  chunk x n/2       double2, the four-step FFT intermediate (8 MiB per stream)
+ *   constant tables               templates, LC class LUT, log2 table (Universal), FFT twiddles
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include "common.cuh"
+#include "tails.h"
+#include "dft.h"
+#include "engine.h"
+
+/* ------------------------------------------------------------------------------------------ */
+static void set_err(stsgpu_ctx *c, const char *what, cudaError_t e)
+{
+	if (c)
+		snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                                                                                  \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) {                                                                          \
+			set_err(ctx, #call, e_);                                                                  \
+			return STSGPU_E_CUDA;                                                                     \
+		}                                                                                                 \
+	} while (0)
+
+extern "C" const char *stsgpu_strerror(int code)
+{
+	switch (code) {
+	case STSGPU_OK: return "success";
+	case STSGPU_E_INVAL: return "invalid argument";
+	case STSGPU_E_NO_DEVICE: return "no usable CUDA device (the engine has no CPU fallback)";
+	case STSGPU_E_CUDA: return "CUDA call failed";
+	case STSGPU_E_NOMEM: return "out of memory";
+	case STSGPU_E_UNSUPPORTED: return "parameter combination not supported by the GPU engine";
+	case STSGPU_E_STATE: return "call sequence error";
+	case STSGPU_E_NCCL: return "NCCL unavailable or failed";
+	case STSGPU_E_RANGE: return "index out of range";
+	default: return "unknown error";
+	}
+}
+
+static char g_create_err[256];
+extern "C" const char *stsgpu_last_error(const stsgpu_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" int stsgpu_abi_version(void) { return STSGPU_ABI_VERSION; }
+
+extern "C" void stsgpu_default_params(stsgpu_params *p)
+{
+	memset(p, 0, sizeof(*p));
+	p->abi_version = STSGPU_ABI_VERSION;
+	p->device = 0;
+	p->n = 1048576;			/* DEFAULT_BITCOUNT, defs.h:125 */
+	p->max_streams = 1024;
+	p->test_mask = STSGPU_ALL_TESTS;
+	p->block_frequency_M = 16384;	/* defs.h:110-115 */
+	p->non_overlapping_m = 9;
+	p->overlapping_m = 9;
+	p->apen_m = 10;
+	p->serial_m = 16;
+	p->linear_complexity_M = 500;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* nonOverlappingTemplateMatchings.c:338-401: keep the m-bit words without self-overlap, ascending */
+static bool template_accepted(uint32_t value, int m)
+{
+	uint8_t A[32];
+	for (int c = 0; c < m; c++)
+		A[c] = (uint8_t) ((value >> (m - 1 - c)) & 1u);
+	for (int i = 1; i < m; i++) {
+		bool overlap = true;
+		if ((A[0] != A[m - 1]) && ((A[0] != A[m - 2]) || (A[1] != A[m - 1]))) {
+			for (int c = 0; c < m - i; c++)
+				if (A[c] != A[c + i]) {
+					overlap = false;
+					break;
+				}
+		}
+		if (overlap)
+			return false;
+	}
+	return true;
+}
+
+/* the X_init() self-disable rules, one line per reference check */
+static uint32_t effective_mask(const stsgpu_params *p, int *universal_L)
+{
+	const int64_t n = p->n;
+	uint32_t en = p->test_mask & STSGPU_ALL_TESTS;
+	const double logn = log((double) n), log2_ = log(2.0);
+	if (n < 100) en &= ~(1u << STSGPU_TEST_FREQUENCY);				/* frequency.c:102 */
+	{
+		const int64_t M = p->block_frequency_M, N = M > 0 ? n / M : 0;		/* blockFrequency.c:109-129 */
+		if (n < 100 || M < 20 || M <= 0.01 * n || N >= 100) en &= ~(1u << STSGPU_TEST_BLOCK_FREQUENCY);
+	}
+	if (n < 100) en &= ~((1u << STSGPU_TEST_CUSUM) | (1u << STSGPU_TEST_RUNS));	/* cusum.c:109 runs.c:114 */
+	if (n < 128) en &= ~(1u << STSGPU_TEST_LONGEST_RUN);				/* longestRunOfOnes.c:261 */
+	if (n / 1024 < 38) en &= ~(1u << STSGPU_TEST_RANK);				/* rank.c:119-128 */
+	if (n < 1000) en &= ~(1u << STSGPU_TEST_DFT);					/* discreteFourierTransform.c:123 */
+	{
+		const int64_t M = n / 8;						/* nonOverlapping...c:211-241 */
+		const int m = p->non_overlapping_m;
+		if (M <= 0.01 * n || m < 8 || m > 15 || m > M) en &= ~(1u << STSGPU_TEST_NON_OVERLAPPING);
+	}
+	{
+		const int64_t N = n / 1032;						/* overlapping...c:151-168 */
+		if (p->overlapping_m != 9 || n < 1000000 || N * 0.070432326346398449744 <= 5)
+			en &= ~(1u << STSGPU_TEST_OVERLAPPING);
+	}
+	int L;										/* universal.c:145-192 */
+	for (L = 7; L <= 16; L++)
+		if (n < (1010LL * (1LL << L) * L))
+			break;
+	L--;
+	*universal_L = L;
+	if (n < 387840 || L < 6 || L > 16) en &= ~(1u << STSGPU_TEST_UNIVERSAL);
+	if (p->apen_m >= lround(floor(logn / log2_ - 5.0))) en &= ~(1u << STSGPU_TEST_APEN);	/* approximateEntropy.c:109 */
+	if (n < 1000000)								/* randomExcursions.c:112 */
+		en &= ~((1u << STSGPU_TEST_RND_EXCURSION) | (1u << STSGPU_TEST_RND_EXCURSION_VAR));
+	if (p->serial_m >= lround(floor(logn / log2_ - 2.0))) en &= ~(1u << STSGPU_TEST_SERIAL);	/* serial.c:112 */
+	{
+		const int64_t M = p->linear_complexity_M, N = M > 0 ? n / M : 0;	/* linearComplexity.c:118-138 */
+		if (n < 1000000 || M < 500 || M > 5000 || N < 200) en &= ~(1u << STSGPU_TEST_LINEARCOMPLEXITY);
+	}
+	return en;
+}
+
+static const struct { int64_t min_n; int M, min_class, max_class; double pi[7]; } lr_rows[3] = {
+	/* longestRunOfOnes.c:148-210 */
+	{ 128, 8, 1, 7, { 0.21484375, 0.3671875, 0.23046875, 0.109375, 0.046875, 0.01953125, 0.01171875 } },
+	{ 6272, 128, 4, 10, { 0.11740357883779323143, 0.24295595927745485921, 0.24936348317907796964,
+			      0.17517706034678234949, 0.10270117130405369391, 0.05521550943390406075,
+			      0.05718333762093383558 } },
+	{ 750000, 10000, 10, 16, { 0.08663231117995278587, 0.20820064838760340198, 0.24841858194169954122,
+				   0.19391278674165693004, 0.12145848508900441468, 0.06801108930393995064,
+				   0.07336609745614297557 } },
+};
+static const double univ_expected[17] = { 0, 0, 0, 0, 0, 0, 5.2177052, 6.1962507, 7.1836656, 8.1764248, 9.1723243,
+	10.170032, 11.168765, 12.168070, 13.167693, 14.167488, 15.167379 };	/* universal.c:72-75 */
+static const double univ_variance[17] = { 0, 0, 0, 0, 0, 0, 2.954, 3.125, 3.238, 3.311, 3.356, 3.384, 3.401, 3.410,
+	3.416, 3.419, 3.421 };							/* universal.c:77-80 */
+
+static int fail_create(stsgpu_ctx *ctx, int code, const char *msg)
+{
+	snprintf(g_create_err, sizeof(g_create_err), "%s%s%s", msg, ctx && ctx->err[0] ? ": " : "",
+		 ctx && ctx->err[0] ? ctx->err : "");
+	if (ctx)
+		stsgpu_destroy(ctx);
+	return code;
+}
+
+template <typename T> static cudaError_t upload(T **dptr, const T *host, size_t count)
+{
+	cudaError_t e = cudaMalloc((void **) dptr, count * sizeof(T));
+	if (e != cudaSuccess)
+		return e;
+	return cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static double2 unit_root(long double num, long double den)	/* exp(-2 pi i num / den) */
+{
+	long double a = -2.0L * 3.14159265358979323846264338327950288L * num / den;
+	return make_double2((double) cosl(a), (double) sinl(a));
+}
+
+extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
+{
+	g_create_err[0] = 0;
+	if (p == NULL || out == NULL || p->abi_version != STSGPU_ABI_VERSION)
+		return fail_create(NULL, STSGPU_E_INVAL, "bad params pointer or ABI version");
+	if (p->n < 8 || (p->n % 8) != 0 || p->max_streams < 1)		/* parse_args.c:939: n must be a multiple of 8 */
+		return fail_create(NULL, STSGPU_E_INVAL, "n must be a positive multiple of 8 and max_streams >= 1");
+	if (p->n > (1LL << 31) - 4096)
+		return fail_create(NULL, STSGPU_E_UNSUPPORTED, "n above 2^31 bits per stream");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= p->device || p->device < 0)
+		return fail_create(NULL, STSGPU_E_NO_DEVICE, "no CUDA device with the requested ordinal");
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
+		return fail_create(NULL, STSGPU_E_NO_DEVICE, "device is not sm_100 (B200) class");
+
+	stsgpu_ctx *ctx = new (std::nothrow) stsgpu_ctx();
+	if (ctx == NULL)
+		return fail_create(NULL, STSGPU_E_NOMEM, "host allocation failed");
+	ctx->prm = *p;
+	ctx->device = p->device;
+	ctx->num_sms = prop.multiProcessorCount;
+	if (cudaSetDevice(p->device) != cudaSuccess)
+		return fail_create(ctx, STSGPU_E_CUDA, "cudaSetDevice failed");
+
+	/* ---- layout (must match oracle_layout_for: same contract, written independently) ---- */
+	stsgpu_layout &lay = ctx->lay;
+	memset(&lay, 0, sizeof(lay));
+	int L = 0;
+	const uint32_t en = effective_mask(p, &L);
+	lay.enabled_mask = en;
+	lay.universal_L = L;
+	const int64_t n = p->n;
+	std::vector<uint32_t> tmpl;
+	if (en & (1u << STSGPU_TEST_NON_OVERLAPPING))
+		for (uint32_t v = 1; v < (1u << p->non_overlapping_m); v++)
+			if (template_accepted(v, p->non_overlapping_m))
+				tmpl.push_back(v);
+	lay.ntemplates = (int32_t) tmpl.size();
+	lay.nw = lay.ntemplates * 8;
+	const int64_t bfN = p->block_frequency_M > 0 ? n / p->block_frequency_M : 0;
+	const int pvc[16] = { 0, 1, 1, 2, 1, 1, 1, 1, lay.ntemplates, 1, 1, 1, 8, 18, 2, 1 };
+	const int stc[16] = { 0, 1, 1 + (int) bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 49, 19, 3, 7 };
+	for (int t = 1; t <= 15; t++) {
+		if (!((en >> t) & 1u))
+			continue;
+		lay.pv_off[t] = lay.npv; lay.pv_cnt[t] = pvc[t]; lay.npv += pvc[t];
+		lay.st_off[t] = lay.nst; lay.st_cnt[t] = stc[t]; lay.nst += stc[t];
+	}
+	if (lay.npv == 0)
+		return fail_create(ctx, STSGPU_E_INVAL, "no test left enabled for these parameters");
+
+	/* ---- device parameters ---- */
+	DevParams &P = ctx->P;
+	memset(&P, 0, sizeof(P));
+	P.n = n;
+	P.nwords = (n + 31) / 32;
+	P.pitch_words = ((P.nwords + 4 + 31) / 32) * 32;
+	P.npv = lay.npv; P.nst = lay.nst; P.nw = lay.nw;
+	for (int t = 0; t < 16; t++) { P.pv_off[t] = lay.pv_off[t]; P.st_off[t] = lay.st_off[t]; }
+	P.enabled = en;
+	P.bf_M = p->block_frequency_M; P.bf_N = bfN;
+	int idx = 0;								/* longestRunOfOnes.c:352-360 */
+	while (idx < 3 && n > lr_rows[idx].min_n) ++idx;
+	if (idx >= 3) idx = 2;
+	P.lr_M = lr_rows[idx].M; P.lr_min_class = lr_rows[idx].min_class; P.lr_max_class = lr_rows[idx].max_class;
+	P.lr_N = n / P.lr_M;
+	P.rank_count = n / 1024;
+	P.nonov_m = p->non_overlapping_m; P.ntemplates = lay.ntemplates; P.nonov_M = n / 8;
+	P.ov_N = n / 1032;
+	P.univ_L = L; P.univ_Q = 10LL << L; P.univ_K = 1000LL << L;		/* universal.c:324-325 */
+	P.apen_m = p->apen_m; P.serial_m = p->serial_m;
+	P.lc_M = p->linear_complexity_M; P.lc_N = P.lc_M > 0 ? n / P.lc_M : 0;
+	{
+		const double mz = 0.005 * sqrt((double) n);			/* driver.c:316 */
+		P.min_zero_crossings = (int64_t) (mz > 500.0 ? mz : 500.0);
+	}
+	const bool want_serial = en & (1u << STSGPU_TEST_SERIAL), want_apen = en & (1u << STSGPU_TEST_APEN);
+	if (want_serial || want_apen) {
+		int H = 0, lowest = 99;
+		if (want_serial) { H = p->serial_m; lowest = p->serial_m - 2 > 1 ? p->serial_m - 2 : 1; }
+		if (want_apen) {
+			if (p->apen_m + 1 > H) H = p->apen_m + 1;
+			if (p->apen_m < lowest) lowest = p->apen_m;
+		}
+		P.hist_bits = H;
+		P.hist_slice_bits = H > 15 ? H - 15 : 0;
+		if (H > 21 || (want_serial && p->serial_m < 3) || (want_apen && p->apen_m < 1) || lowest < P.hist_slice_bits)
+			return fail_create(ctx, STSGPU_E_UNSUPPORTED,
+					   "Serial/ApEn block lengths outside the engine's range (3 <= serial m <= 21, "
+					   "1 <= apen m <= 20, levels spread < 15 bits)");
+	}
+	if ((en & (1u << STSGPU_TEST_UNIVERSAL)) && L > 15)
+		return fail_create(ctx, STSGPU_E_UNSUPPORTED, "Universal test with L = 16 (n >= 1.06e9 bits) is not supported");
+	int logn = 0;
+	while ((1LL << logn) < n) logn++;
+	if (en & (1u << STSGPU_TEST_DFT)) {
+		if ((1LL << logn) != n || logn < 10 || logn > 20)
+			return fail_create(ctx, STSGPU_E_UNSUPPORTED,
+					   "DFT test needs n = 2^k with 10 <= k <= 20 in this build; clear bit 7 of test_mask");
+	}
+
+	/* ---- tail constants (host libm, reference expressions) ---- */
+	TailConsts &K = ctx->K;
+	memset(&K, 0, sizeof(K));
+	K.sqrt2 = sqrt(2.0); K.log2_ = log(2.0); K.sqrtn = sqrt((double) n);	/* driver.c:304-310 */
+	K.two_over_sqrtn = 2.0 / K.sqrtn;					/* runs.c:139 */
+	K.sqrt2n = sqrt(2.0 * (double) n);					/* runs.c:138 */
+	K.lgam_bf = lgamma(bfN / 2.0);
+	K.lgam_3 = lgamma(3.0); K.lgam_4 = lgamma(4.0); K.lgam_2_5 = lgamma(2.5);
+	K.lgam_apen = lgamma((double) (1LL << (p->apen_m > 0 ? p->apen_m - 1 : 0)));
+	K.lgam_serial1 = lgamma((double) (1LL << (p->serial_m > 1 ? p->serial_m - 1 : 0)) / 2.0);
+	K.lgam_serial2 = lgamma((double) (1LL << (p->serial_m > 2 ? p->serial_m - 2 : 0)) / 2.0);
+	for (int pass = 0; pass < 2; pass++) {					/* rank.c:131-170 */
+		const int r = 32 - pass;
+		double product = 1.0;
+		for (int i = 0; i <= r - 1; i++)
+			product *= ((1.0 - pow(2.0, i - 32)) * (1.0 - pow(2.0, i - 32))) / (1.0 - pow(2.0, i - r));
+		const double v = pow(2.0, r * (32 + 32 - r) - 32 * 32) * product;
+		if (pass == 0) K.p_32 = v; else K.p_31 = v;
+	}
+	K.p_30 = 1.0 - (K.p_32 + K.p_31);					/* rank.c:172 */
+	for (int i = 0; i < 7; i++) K.lr_pi[i] = lr_rows[idx].pi[i];
+	K.sqrtn4_095_005 = sqrt((double) n / 4.0 * 0.95 * 0.05);		/* discreteFourierTransform.c:141 */
+	{
+		const long M = (long) (n / 8), m = p->non_overlapping_m;	/* nonOverlapping...c:479-480 */
+		if (m >= 1 && m <= 30) {
+			K.nonov_mu = (M - m + 1) / ((double) ((long) 1 << m));
+			const double sigma_squared =
+				M * (1.0 / ((double) ((long) 1 << m)) - (2.0 * m - 1.0) / ((double) ((long) 1 << m * 2)));
+			K.nonov_sqrt_sigma2 = sqrt(sigma_squared);
+		}
+	}
+	{
+		const double ov[6] = { 0.36409105321672786245, 0.18565890010624038178, 0.13938113045903269914,
+				       0.10057114399877811497, 0.070432326346398449744, 0.13986544587282249192 };
+		for (int i = 0; i < 6; i++) K.ov_pi[i] = ov[i];			/* overlapping...c:71-78 */
+	}
+	if (L >= 6 && L <= 16) {						/* universal.c:385-386 */
+		const double Kd = (double) P.univ_K;
+		const double c = 0.7 - 0.8 / (double) L + (4 + 32 / (double) L) * pow(Kd, -3.0 / (double) L) / 15;
+		K.univ_sigma = c * sqrt(univ_variance[L] / Kd);
+		K.univ_expected = univ_expected[L];
+	}
+	for (int i = 1; i <= 4; i++) K.rex_pi[i - 1][0] = 1.0 - 1.0 / (2.0 * i);	/* randomExcursions.c:187-207 */
+	for (int j = 1; j < 5; j++)
+		for (int i = 1; i <= 4; i++)
+			K.rex_pi[i - 1][j] = 1.0 / (4.0 * i * i) * pow(K.rex_pi[i - 1][0], j - 1);
+	for (int i = 1; i <= 4; i++) K.rex_pi[i - 1][5] = 1.0 / (2.0 * i) * pow(K.rex_pi[i - 1][0], 4);
+	{
+		const double lc[7] = { 0.01047, 0.03125, 0.12500, 0.50000, 0.25000, 0.06250, 0.020833 };
+		for (int i = 0; i < 7; i++) K.lc_pi[i] = lc[i];			/* linearComplexity.c:62 */
+	}
+
+	/* ---- device allocations ---- */
+	const int64_t B = p->max_streams;
+	ctx->in_bytes = (size_t) B * P.pitch_words * 4;
+#define CKC(call, what)                                                                                           \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) {                                                                          \
+			set_err(ctx, what, e_);                                                                   \
+			return fail_create(ctx, e_ == cudaErrorMemoryAllocation ? STSGPU_E_NOMEM : STSGPU_E_CUDA, \
+					   "stsgpu_create");                                                      \
+		}                                                                                                 \
+	} while (0)
+	CKC(cudaMalloc((void **) &ctx->d_in, ctx->in_bytes), "cudaMalloc(input)");
+	CKC(cudaMemset(ctx->d_in, 0, ctx->in_bytes), "cudaMemset(input)");
+	CKC(cudaMalloc((void **) &ctx->d_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMalloc(pvals)");
+	CKC(cudaMalloc((void **) &ctx->d_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMalloc(istats)");
+	CKC(cudaMalloc((void **) &ctx->d_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMalloc(wcount)");
+	CKC(cudaMallocHost((void **) &ctx->h_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMallocHost(pvals)");
+	CKC(cudaMallocHost((void **) &ctx->h_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMallocHost(istats)");
+	CKC(cudaMallocHost((void **) &ctx->h_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMallocHost(wcount)");
+	if (!tmpl.empty())
+		CKC(upload(&ctx->d_templates, tmpl.data(), tmpl.size()), "upload(templates)");
+	if (want_apen)
+		CKC(cudaMalloc((void **) &ctx->d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
+		    "cudaMalloc(apen histograms)");
+	if (en & (1u << STSGPU_TEST_LINEARCOMPLEXITY)) {
+		/*
+		 * class of every possible L (linearComplexity.c:356-377), evaluated on the host by the
+		 * reference's expression.  `1 << M` on an int is undefined for M >= 32; x86-64 gcc takes the
+		 * count mod 32, which is what every build of the reference does and what is reproduced here.
+		 */
+		const int M = (int) P.lc_M;
+		std::vector<uint8_t> lut((size_t) M + 2);
+		const double two_pow = (double) (int) (1u << (M & 31));
+		const double mean = (M / 2.0) + (((M + 1) % 2) ? 10 : 8) / 36.0 - (M / 3.0 + 2.0 / 9.0) / two_pow;
+		for (int Lc = 0; Lc <= M; Lc++) {
+			const double T = ((M % 2) ? (mean - Lc) : (Lc - mean)) + 2.0 / 9.0;
+			const double cls = (double) (6 - 1) / 2.0;
+			int v;
+			if (T <= -cls) v = 0;
+			else if (T > cls) v = 6;
+			else v = (int) ceil(T + cls);
+			lut[Lc] = (uint8_t) v;
+		}
+		CKC(upload(&ctx->d_class_lut, lut.data(), lut.size()), "upload(LC class table)");
+	}
+	if (en & (1u << STSGPU_TEST_UNIVERSAL)) {
+		/* universal.c:369: log(i - T[.]) / log(2), one table entry per possible distance */
+		const int64_t cnt = P.univ_Q + P.univ_K + 1;
+		std::vector<double> tab((size_t) cnt);
+		tab[0] = 0.0;
+		for (int64_t d = 1; d < cnt; d++)
+			tab[d] = log((double) d) / K.log2_;
+		CKC(upload(&ctx->d_log2tab, tab.data(), tab.size()), "upload(log2 table)");
+	}
+	if (en & (1u << STSGPU_TEST_DFT)) {
+		DftPlan &D = ctx->dft;
+		const int logN = logn - 1;
+		D.logN2 = (logN + 1) / 2 > 10 ? 10 : (logN + 1) / 2;
+		D.logN1 = logN - D.logN2;
+		const int N1 = 1 << D.logN1, N2 = 1 << D.logN2;
+		const int64_t N = (int64_t) N1 * N2;
+		int cw = 512 / N1 > 8 ? 512 / N1 : 8;
+		if (cw > N2) cw = N2;
+		D.cw = cw;
+		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
+		std::vector<double2> wm(1024), tl(1024), th((size_t) (N >= 1024 ? N / 1024 : 1)), p1(N1), p2(N2);
+		for (int k = 0; k < 1024; k++) { wm[k] = unit_root(k, 1024); tl[k] = unit_root(k, (long double) N); }
+		for (size_t k = 0; k < th.size(); k++) th[k] = unit_root((long double) k * 1024, (long double) N);
+		for (int k = 0; k < N1; k++) p1[k] = unit_root(k, (long double) n);
+		for (int k = 0; k < N2; k++) p2[k] = unit_root((long double) N1 * k, (long double) n);
+		double2 *d;
+		CKC(upload(&d, wm.data(), wm.size()), "upload(fft wm)"); D.wm = d; ctx->dft_tabs[0] = d;
+		CKC(upload(&d, tl.data(), tl.size()), "upload(fft tl)"); D.tl = d; ctx->dft_tabs[1] = d;
+		CKC(upload(&d, th.data(), th.size()), "upload(fft th)"); D.th = d; ctx->dft_tabs[2] = d;
+		CKC(upload(&d, p1.data(), p1.size()), "upload(fft p1)"); D.p1 = d; ctx->dft_tabs[3] = d;
+		CKC(upload(&d, p2.data(), p2.size()), "upload(fft p2)"); D.p2 = d; ctx->dft_tabs[4] = d;
+		int64_t chunk = 16;
+		const char *envc = getenv("STSGPU_DFT_CHUNK");
+		if (envc && atoi(envc) > 0) chunk = atoi(envc);
+		if (chunk > B) chunk = B;
+		ctx->dft_chunk = chunk;
+		CKC(cudaMalloc((void **) &ctx->d_dft_work, (size_t) chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
+	}
+	CKC(cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking), "cudaStreamCreate");
+	for (int i = 0; i < STS_AUX_STREAMS; i++) {
+		CKC(cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking), "cudaStreamCreate");
+		CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming), "cudaEventCreate");
+	}
+	CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+	CKC(cudaEventCreate(&ctx->ev_start), "cudaEventCreate");
+	CKC(cudaEventCreate(&ctx->ev_end), "cudaEventCreate");
+	for (int i = 0; i < STS_MAX_KERNELS; i++) {
+		CKC(cudaEventCreate(&ctx->k_ev0[i]), "cudaEventCreate");
+		CKC(cudaEventCreate(&ctx->k_ev1[i]), "cudaEventCreate");
+	}
+#undef CKC
+	*out = ctx;
+	return STSGPU_OK;
+}
+
+extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
+{
+	if (ctx == NULL)
+		return;
+	cudaSetDevice(ctx->device);
+	if (ctx->s_main) cudaStreamSynchronize(ctx->s_main);
+	stsgpu_comm_destroy_internal(ctx);
+	cudaFree(ctx->d_in); cudaFree(ctx->d_pv); cudaFree(ctx->d_st); cudaFree(ctx->d_w);
+	cudaFreeHost(ctx->h_pv); cudaFreeHost(ctx->h_st); cudaFreeHost(ctx->h_w);
+	cudaFree(ctx->d_templates); cudaFree(ctx->d_apen_hist); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab);
+	cudaFree(ctx->d_dft_work); cudaFree(ctx->d_debug);
+	for (int i = 0; i < 5; i++) cudaFree(ctx->dft_tabs[i]);
+	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+	for (int i = 0; i < STS_AUX_STREAMS; i++) {
+		if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
+		if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+	}
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+	if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+	for (int i = 0; i < STS_MAX_KERNELS; i++) {
+		if (ctx->k_ev0[i]) cudaEventDestroy(ctx->k_ev0[i]);
+		if (ctx->k_ev1[i]) cudaEventDestroy(ctx->k_ev1[i]);
+	}
+	delete ctx;
+}
+
+extern "C" int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out)
+{
+	if (ctx == NULL || out == NULL)
+		return STSGPU_E_INVAL;
+	*out = ctx->lay;
+	return STSGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+struct Group {
+	const char *name;
+	int stream;		/* -1: main, else aux index */
+};
+
+static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
+{
+	const DevParams &P = ctx->P;
+	const stsgpu_layout &lay = ctx->lay;
+	cudaStream_t sm = ctx->s_main;
+	CK(cudaMemsetAsync(ctx->d_st, 0, (size_t) nstreams * lay.nst * sizeof(long long), sm));
+	CK(cudaEventRecord(ctx->ev_start, sm));
+	ctx->nkernels = 0;
+	const bool prof = ctx->profiling;
+
+	LaunchCtx L;
+	L.d_in = ctx->d_in; L.d_pv = ctx->d_pv; L.d_st = ctx->d_st; L.d_w = ctx->d_w;
+	L.nstreams = nstreams; L.num_sms = ctx->num_sms;
+
+	if (!prof) {
+		CK(cudaEventRecord(ctx->ev_fork, sm));
+		for (int i = 0; i < STS_AUX_STREAMS; i++)
+			CK(cudaStreamWaitEvent(ctx->s_aux[i], ctx->ev_fork, 0));
+	}
+	/* kernel groups; without profiling they run concurrently on four streams */
+	enum { G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_PATTERN, G_UNIVERSAL, G_LC, G_DFT, G_COUNT };
+	static const Group groups[G_COUNT] = {
+		{ "scan(freq,cusum,runs,excursions)", -1 }, { "blocks(blockfreq,longestrun,overlapping)", -1 },
+		{ "rank", -1 }, { "nonoverlapping", -1 }, { "pattern(serial,apen)", 2 }, { "universal", 2 },
+		{ "linear_complexity", 0 }, { "dft", 1 },
+	};
+	for (int g = 0; g < G_COUNT; g++) {
+		L.stream = (prof || groups[g].stream < 0) ? sm : ctx->s_aux[groups[g].stream];
+		const int slot = ctx->nkernels;
+		if (prof)
+			CK(cudaEventRecord(ctx->k_ev0[slot], L.stream));
+		cudaError_t e = cudaSuccess;
+		int64_t launched = 0;
+		switch (g) {
+		case G_SCAN: e = launch_scan(P, L); launched = 1; break;
+		case G_BLOCKS: e = launch_blocks(P, L); launched = 3; break;
+		case G_RANK: e = launch_rank(P, L); launched = 1; break;
+		case G_NONOV: e = launch_nonoverlapping(P, L, ctx->d_templates); launched = 1; break;
+		case G_PATTERN: e = launch_pattern(P, L, ctx->d_apen_hist); launched = 1; break;
+		case G_UNIVERSAL: e = launch_universal(P, L, ctx->d_log2tab); launched = 1; break;
+		case G_LC: e = launch_lc(P, L, ctx->d_class_lut); launched = 1; break;
+		case G_DFT:
+			e = launch_dft(P, L, ctx->dft, ctx->d_dft_work, ctx->dft_chunk);
+			launched = (P.enabled & (1u << STSGPU_TEST_DFT)) ? 2 * ((nstreams + ctx->dft_chunk - 1) / ctx->dft_chunk) : 0;
+			break;
+		}
+		if (e != cudaSuccess) {
+			set_err(ctx, groups[g].name, e);
+			return STSGPU_E_CUDA;
+		}
+		ctx->launches += launched;
+		if (prof) {
+			CK(cudaEventRecord(ctx->k_ev1[slot], L.stream));
+			ctx->k_name[slot] = groups[g].name;
+			ctx->nkernels++;
+		}
+	}
+	if (!prof) {
+		for (int i = 0; i < STS_AUX_STREAMS; i++) {
+			CK(cudaEventRecord(ctx->ev_join[i], ctx->s_aux[i]));
+			CK(cudaStreamWaitEvent(sm, ctx->ev_join[i], 0));
+		}
+	}
+	L.stream = sm;
+	{
+		const int slot = ctx->nkernels;
+		if (prof)
+			CK(cudaEventRecord(ctx->k_ev0[slot], sm));
+		cudaError_t e = launch_tails(P, ctx->K, L, ctx->d_apen_hist);
+		if (e != cudaSuccess) {
+			set_err(ctx, "tails", e);
+			return STSGPU_E_CUDA;
+		}
+		ctx->launches += 1;
+		if (prof) {
+			CK(cudaEventRecord(ctx->k_ev1[slot], sm));
+			ctx->k_name[slot] = "tails(p-values)";
+			ctx->nkernels++;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev_end, sm));
+	CK(cudaMemcpyAsync(ctx->h_pv, ctx->d_pv, (size_t) nstreams * lay.npv * sizeof(double), cudaMemcpyDeviceToHost, sm));
+	CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sm));
+	if (lay.nw)
+		CK(cudaMemcpyAsync(ctx->h_w, ctx->d_w, (size_t) nstreams * lay.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, sm));
+	ctx->cur_nstreams = nstreams;
+	ctx->cur_first = first_iteration;
+	ctx->in_flight = true;
+	ctx->have_results = false;
+	return STSGPU_OK;
+}
+
+static int check_batch(stsgpu_ctx *ctx, int64_t nstreams)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (nstreams < 1 || nstreams > ctx->prm.max_streams) {
+		snprintf(ctx->err, sizeof(ctx->err), "nstreams %lld outside 1..max_streams", (long long) nstreams);
+		return STSGPU_E_RANGE;
+	}
+	if (ctx->in_flight) {
+		snprintf(ctx->err, sizeof(ctx->err), "a batch is still in flight: call stsgpu_wait first");
+		return STSGPU_E_STATE;
+	}
+	if (cudaSetDevice(ctx->device) != cudaSuccess)
+		return STSGPU_E_CUDA;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_upload(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams)
+{
+	int rc = check_batch(ctx, nstreams);
+	if (rc) return rc;
+	if (raw == NULL) return STSGPU_E_INVAL;
+	const size_t row = (size_t) (ctx->P.n / 8);
+	CK(cudaMemcpy2DAsync(ctx->d_in, (size_t) ctx->P.pitch_words * 4, raw, row, row, (size_t) nstreams,
+			     cudaMemcpyHostToDevice, ctx->s_main));
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams, int64_t first_iteration)
+{
+	int rc = stsgpu_upload(ctx, raw, nstreams);
+	if (rc) return rc;
+	return run_tests(ctx, nstreams, first_iteration);
+}
+
+extern "C" int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
+{
+	int rc = check_batch(ctx, nstreams);
+	if (rc) return rc;
+	return run_tests(ctx, nstreams, first_iteration);
+}
+
+extern "C" int stsgpu_wait(stsgpu_ctx *ctx)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->in_flight) {
+		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_wait without a submitted batch");
+		return STSGPU_E_STATE;
+	}
+	cudaSetDevice(ctx->device);
+	ctx->in_flight = false;
+	CK(cudaStreamSynchronize(ctx->s_main));
+	for (int i = 0; i < STS_AUX_STREAMS; i++)
+		CK(cudaStreamSynchronize(ctx->s_aux[i]));
+	CK(cudaGetLastError());
+	ctx->have_results = true;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first_iteration, const double **pvals,
+			      const int64_t **istats, const uint32_t **wcount)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->have_results) {
+		snprintf(ctx->err, sizeof(ctx->err), "no completed batch");
+		return STSGPU_E_STATE;
+	}
+	if (nstreams) *nstreams = ctx->cur_nstreams;
+	if (first_iteration) *first_iteration = ctx->cur_first;
+	if (pvals) *pvals = ctx->h_pv;
+	if (istats) *istats = (const int64_t *) ctx->h_st;
+	if (wcount) *wcount = ctx->h_w;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_t nstreams)
+{
+	int rc = check_batch(ctx, nstreams);
+	if (rc) return rc;
+	if (first_stream < 0) return STSGPU_E_INVAL;
+	cudaError_t e = launch_lcg(ctx->P, ctx->d_in, first_stream, nstreams, ctx->s_main);
+	if (e != cudaSuccess) {
+		set_err(ctx, "lcg", e);
+		return STSGPU_E_CUDA;
+	}
+	ctx->launches += 1;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_download_input(stsgpu_ctx *ctx, uint8_t *raw, int64_t nstreams)
+{
+	int rc = check_batch(ctx, nstreams);
+	if (rc) return rc;
+	if (raw == NULL) return STSGPU_E_INVAL;
+	const size_t row = (size_t) (ctx->P.n / 8);
+	CK(cudaMemcpy2DAsync(raw, row, ctx->d_in, (size_t) ctx->P.pitch_words * 4, row, (size_t) nstreams,
+			     cudaMemcpyDeviceToHost, ctx->s_main));
+	CK(cudaStreamSynchronize(ctx->s_main));
+	return STSGPU_OK;
+}
+
+extern "C" void *stsgpu_host_alloc(size_t bytes)
+{
+	void *p = NULL;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess)
+		return NULL;
+	return p;
+}
+extern "C" void stsgpu_host_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" int stsgpu_set_profiling(stsgpu_ctx *ctx, int on)
+{
+	if (ctx == NULL) return STSGPU_E_INVAL;
+	ctx->profiling = on != 0;
+	return STSGPU_OK;
+}
+extern "C" int stsgpu_kernel_count(const stsgpu_ctx *ctx) { return ctx ? ctx->nkernels : 0; }
+extern "C" int stsgpu_kernel_info(stsgpu_ctx *ctx, int i, const char **name, float *ms)
+{
+	if (ctx == NULL || i < 0 || i >= ctx->nkernels) return STSGPU_E_RANGE;
+	if (name) *name = ctx->k_name[i];
+	if (ms) {
+		*ms = 0.f;
+		CK(cudaEventElapsedTime(ms, ctx->k_ev0[i], ctx->k_ev1[i]));
+	}
+	return STSGPU_OK;
+}
+extern "C" int stsgpu_last_batch_ms(stsgpu_ctx *ctx, float *ms)
+{
+	if (ctx == NULL || ms == NULL) return STSGPU_E_INVAL;
+	if (!ctx->have_results) return STSGPU_E_STATE;
+	CK(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_end));
+	return STSGPU_OK;
+}
+extern "C" int64_t stsgpu_launch_count(const stsgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int stsgpu_debug_pattern_histogram(stsgpu_ctx *ctx, int64_t s, int bits, uint32_t *hist)
+{
+	int rc = check_batch(ctx, 1);
+	if (rc) return rc;
+	if (hist == NULL || bits < 1 || bits > 21 || s < 0 || s >= ctx->prm.max_streams) return STSGPU_E_INVAL;
+	if (ctx->d_debug == NULL)
+		CK(cudaMalloc((void **) &ctx->d_debug, sizeof(uint32_t) << 21));
+	LaunchCtx L;
+	L.stream = ctx->s_main; L.d_in = ctx->d_in; L.d_pv = ctx->d_pv; L.d_st = ctx->d_st; L.d_w = ctx->d_w;
+	L.nstreams = 1; L.num_sms = ctx->num_sms;
+	cudaError_t e = launch_debug_histogram(ctx->P, L, s, bits, ctx->d_debug);
+	if (e != cudaSuccess) {
+		set_err(ctx, "debug histogram", e);
+		return STSGPU_E_CUDA;
+	}
+	CK(cudaMemcpyAsync(hist, ctx->d_debug, sizeof(uint32_t) << bits, cudaMemcpyDeviceToHost, ctx->s_main));
+	CK(cudaStreamSynchronize(ctx->s_main));
+	return STSGPU_OK;
+}

@@ -1,0 +1,63 @@
+/* engine.h - the context behind the opaque stsgpu_ctx of include/stsgpu.h */
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "tails.h"
+#include "dft.h"
+
+#define STS_AUX_STREAMS 3
+
+struct stsgpu_ctx {
+	stsgpu_params prm;
+	stsgpu_layout lay;
+	DevParams P;
+	TailConsts K;
+	DftPlan dft;
+	int device = 0, num_sms = 0;
+
+	cudaStream_t s_main = nullptr, s_aux[STS_AUX_STREAMS] = { nullptr, nullptr, nullptr };
+	cudaEvent_t ev_fork = nullptr, ev_join[STS_AUX_STREAMS] = { nullptr, nullptr, nullptr };
+	cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+
+	uint32_t *d_in = nullptr;
+	size_t in_bytes = 0;
+	double *d_pv = nullptr;
+	long long *d_st = nullptr;
+	uint32_t *d_w = nullptr;
+	double *h_pv = nullptr;
+	long long *h_st = nullptr;
+	uint32_t *h_w = nullptr;
+
+	uint32_t *d_templates = nullptr;
+	uint32_t *d_apen_hist = nullptr;
+	uint8_t *d_class_lut = nullptr;
+	double *d_log2tab = nullptr;
+	double2 *d_dft_work = nullptr;
+	double2 *dft_tabs[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	int64_t dft_chunk = 0;
+	uint32_t *d_debug = nullptr;
+
+	int64_t cur_nstreams = 0, cur_first = 0;
+	bool in_flight = false, have_results = false;
+
+	bool profiling = false;
+	int nkernels = 0;
+	const char *k_name[STS_MAX_KERNELS] = { nullptr };
+	cudaEvent_t k_ev0[STS_MAX_KERNELS] = { nullptr }, k_ev1[STS_MAX_KERNELS] = { nullptr };
+	int64_t launches = 0;
+
+	/* NCCL (comm.cu) */
+	void *nccl_comm = nullptr;
+	int rank = 0, nranks = 1;
+	double *d_gather = nullptr, *h_gather = nullptr;
+	size_t gather_cap = 0;
+
+	char err[256] = { 0 };
+};
+
+void stsgpu_comm_destroy_internal(stsgpu_ctx *ctx);
+
+cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist);
+cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
+cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);
+cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits, uint32_t *d_out);

@@ -1,0 +1,155 @@
+/*
+ * k_lc.cu - linear complexity test: Berlekamp-Massey over GF(2) per M-bit block
+ * (linearComplexity.c:283-377).
+ *
+ * One block per THREAD, bit-packed 32 coefficients per register.  The recurrence is kept in
+ * "sequence-aligned reversed" form so that only one array moves per step:
+ *     Cr_N[j] = c_{N-j}           the connection polynomial reversed and aligned under s_0..s_N
+ *     d_N     = parity(popc(Cr_N & S))                         (linearComplexity.c:312-316)
+ *     on d_N = 1:  Cr_N ^= Br   where Br = Cr_m saved at the last length change stays fixed
+ *                  (x^{N-m} b(x) reversed and aligned at N is exactly Cr_m)   (:322-327)
+ *                  if L <= N/2: L = N + 1 - L, m = N, Br = old Cr_N            (:331-336)
+ *     N -> N + 1:  Cr shifts by one position
+ * All updates are branch-free masks, so the 32 blocks of a warp stay converged.  Positions are
+ * stored with an offset of one (index 0 = position -1) because the initial b(x) = 1 with m = -1
+ * sits at position -1.  The statistic per block is the class of L, looked up in a table computed
+ * on the host with the reference's own expression, including its `1 << M` quirk (:356-377).
+ *
+ * Algorithmic bytes: n/8 per stream.  Integer work: M steps x ~4.5 word-ops x ceil((M+1)/32) words.
+ */
+#include "common.cuh"
+
+#define LC_THREADS 128
+
+template <int W>
+__global__ void __launch_bounds__(LC_THREADS)
+lc_kernel_reg(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
+	      long long *__restrict__ st)
+{
+	__shared__ unsigned int cls[7];
+	const int64_t s = blockIdx.x;
+	if (threadIdx.x < 7)
+		cls[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int M = (int) P.lc_M;
+	const int64_t blk = (int64_t) blockIdx.y * LC_THREADS + threadIdx.x;
+	if (blk < P.lc_N) {
+		const int64_t start = blk * M;
+		uint32_t S[W], C[W], B[W];
+		/* index k of the arrays <-> position k - 1; index 0 (position -1) is masked off in S */
+#pragma unroll
+		for (int i = 0; i < W; i++) {
+			uint32_t v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * i - 1);
+			int valid = M + 1 - 32 * i;			/* indices still inside the block */
+			if (valid < 32)
+				v &= mask_below((uint32_t) (valid > 0 ? valid : 0));
+			S[i] = v;
+			C[i] = 0;
+			B[i] = 0;
+		}
+		C[0] = 0x40000000u;	/* c_0 at position 0  (index 1) */
+		B[0] = 0x80000000u;	/* b_0 at position -1 (index 0) */
+		int L = 0;
+		for (int N = 0; N < M; N++) {
+			uint32_t acc = 0;
+#pragma unroll
+			for (int i = 0; i < W; i++)
+				acc ^= C[i] & S[i];
+			const uint32_t d = (uint32_t) __popc(acc) & 1u;
+			const uint32_t dm = 0u - d;
+			const uint32_t um = (2 * L <= N) ? dm : 0u;
+			uint32_t prev = 0;
+#pragma unroll
+			for (int i = 0; i < W; i++) {
+				const uint32_t c_old = C[i];
+				const uint32_t c_new = c_old ^ (B[i] & dm);
+				B[i] = (c_old & um) | (B[i] & ~um);
+				C[i] = (c_new >> 1) | (prev << 31);	/* advance to N + 1 */
+				prev = c_new;
+			}
+			L = um ? (N + 1 - L) : L;
+		}
+		atomicAdd(&cls[class_lut[L]], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 7 && cls[threadIdx.x])
+		atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
+			  (unsigned long long) cls[threadIdx.x]);
+}
+
+/* any M up to 5000: the same recurrence with the arrays in (L1-resident) local memory */
+#define LC_MAXW 160
+__global__ void __launch_bounds__(LC_THREADS)
+lc_kernel_generic(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
+		  long long *__restrict__ st)
+{
+	__shared__ unsigned int cls[7];
+	const int64_t s = blockIdx.x;
+	if (threadIdx.x < 7)
+		cls[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int M = (int) P.lc_M;
+	const int W = (M + 1 + 31) >> 5;
+	const int64_t blk = (int64_t) blockIdx.y * LC_THREADS + threadIdx.x;
+	if (blk < P.lc_N) {
+		const int64_t start = blk * M;
+		uint32_t S[LC_MAXW], C[LC_MAXW], B[LC_MAXW];
+		for (int i = 0; i < W; i++) {
+			uint32_t v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * i - 1);
+			int valid = M + 1 - 32 * i;
+			if (valid < 32)
+				v &= mask_below((uint32_t) (valid > 0 ? valid : 0));
+			S[i] = v;
+			C[i] = 0;
+			B[i] = 0;
+		}
+		C[0] = 0x40000000u;
+		B[0] = 0x80000000u;
+		int L = 0;
+		for (int N = 0; N < M; N++) {
+			/* only words up to position N carry coefficients */
+			const int hi = min(W - 1, (N + 2) >> 5);
+			uint32_t acc = 0;
+			for (int i = 0; i <= hi; i++)
+				acc ^= C[i] & S[i];
+			const uint32_t d = (uint32_t) __popc(acc) & 1u;
+			const uint32_t dm = 0u - d;
+			const uint32_t um = (2 * L <= N) ? dm : 0u;
+			uint32_t prev = 0;
+			for (int i = 0; i <= hi; i++) {
+				const uint32_t c_old = C[i];
+				const uint32_t c_new = c_old ^ (B[i] & dm);
+				B[i] = (c_old & um) | (B[i] & ~um);
+				C[i] = (c_new >> 1) | (prev << 31);
+				prev = c_new;
+			}
+			if (hi + 1 < W)
+				C[hi + 1] |= prev << 31;	/* bit shifted across the active boundary */
+			L = um ? (N + 1 - L) : L;
+		}
+		atomicAdd(&cls[class_lut[L]], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 7 && cls[threadIdx.x])
+		atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
+			  (unsigned long long) cls[threadIdx.x]);
+}
+
+cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_class_lut)
+{
+	if (!(P.enabled & (1u << STSGPU_TEST_LINEARCOMPLEXITY)))
+		return cudaSuccess;
+	dim3 grid((unsigned) L.nstreams, (unsigned) ((P.lc_N + LC_THREADS - 1) / LC_THREADS));
+	const int W = (int) ((P.lc_M + 1 + 31) >> 5);
+	if (W <= 16)
+		lc_kernel_reg<16><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+	else if (W <= 24)
+		lc_kernel_reg<24><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+	else if (W <= 32)
+		lc_kernel_reg<32><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+	else
+		lc_kernel_generic<<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+	return cudaGetLastError();
+}

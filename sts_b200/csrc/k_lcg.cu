@@ -1,0 +1,61 @@
+/*
+ * k_lcg.cu - the synthetic input: generator 1 (LCG) of the reference's tools/generators.c, produced
+ * directly into the engine's device input buffer.
+ *
+ * generators.c:797-831 iterates x <- 950706376 x mod (2^31 - 1) from x0 = 23482349 in doubles (exact
+ * below 2^53, so identical to integer arithmetic); output bit k (k = 0, 1, ...) is x_{k+1} >= 2^30
+ * (:870-882, DUNIF >= 0.5); write_sequence packs bit 8j + c of the sequence into bit c of file byte
+ * j (LSB first, :1640-1660), and the state carries over from stream to stream.  One thread makes
+ * one 32-bit word of the file: it jumps to its position with a^k mod p by square-and-multiply and
+ * then steps 32 times.  A little-endian 32-bit store of "bit i = sequence bit 32 t + i" is exactly
+ * the 4 file bytes.
+ */
+#include "common.cuh"
+
+#define LCG_A 950706376ull
+#define LCG_P 2147483647ull
+#define LCG_X0 23482349ull
+
+__device__ __forceinline__ uint64_t mulmod31(uint64_t a, uint64_t b)
+{
+	uint64_t v = a * b;			/* < 2^62 */
+	v = (v & LCG_P) + (v >> 31);
+	v = (v & LCG_P) + (v >> 31);
+	return v >= LCG_P ? v - LCG_P : v;
+}
+
+__global__ void __launch_bounds__(256)
+lcg_kernel(DevParams P, uint32_t *__restrict__ out, int64_t first_stream, int64_t nstreams)
+{
+	const int64_t words_per_stream = P.nwords;
+	const int64_t gid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= nstreams * words_per_stream)
+		return;
+	const int64_t s = gid / words_per_stream, t = gid % words_per_stream;
+	const uint64_t k0 = (uint64_t) ((first_stream + s) * P.n + 32 * t);	/* index of my first output bit */
+	/* state before producing bit k0 is x_{k0} = a^{k0} x0 */
+	uint64_t x = LCG_X0, base = LCG_A, e = k0;
+	while (e) {
+		if (e & 1ull)
+			x = mulmod31(x, base);
+		base = mulmod31(base, base);
+		e >>= 1;
+	}
+	const int64_t rem = P.n - 32 * t;
+	const int valid = rem >= 32 ? 32 : (int) rem;
+	uint32_t word = 0;
+	for (int i = 0; i < valid; i++) {
+		x = mulmod31(x, LCG_A);
+		if (x >= (1ull << 30))
+			word |= 1u << i;
+	}
+	out[s * P.pitch_words + t] = word;
+}
+
+cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream)
+{
+	const int64_t total = nstreams * P.nwords;
+	const unsigned blocks = (unsigned) ((total + 255) / 256);
+	lcg_kernel<<<blocks, 256, 0, stream>>>(P, d_in, first_stream, nstreams);
+	return cudaGetLastError();
+}

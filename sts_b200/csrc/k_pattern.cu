@@ -1,0 +1,231 @@
+/*
+ * k_pattern.cu - the m-bit pattern histogram family.
+ *
+ * (1) NonOverlappingTemplateMatchings (nonOverlappingTemplateMatchings.c:495-575).  The accepted
+ *     templates have no self-overlap (appendTemplate :374-395), so the reference's greedy scan
+ *     "count a hit, skip m bits" counts every occurrence: W[t][i] is bin value(t) of the 2^m-bin
+ *     histogram of all m-bit windows lying inside block i (positions 0 .. M-m).  One CTA builds
+ *     that histogram for one (stream, block) in shared memory with a sliding funnel-shift window
+ *     and gathers the bins of all templates: the whole template set costs one pass.
+ *
+ * (2) Serial (serial.c:390-419) and ApproximateEntropy (approximateEntropy.c:369-407) both count
+ *     all n cyclic windows; because the windowing is cyclic, hist_{b-1}[x] = hist_b[2x] + hist_b[2x+1]
+ *     exactly, so ONE histogram at H = max(serial_m, apen_m + 1) bits gives every level by folding.
+ *     H can reach 21 bits (8 MiB of counters): a CTA owns the patterns whose top (H - 15) bits equal
+ *     its slice index and keeps 2^min(H,15) 32-bit counters (<= 128 KiB) in shared memory.
+ *     Serial leaves the kernel as exact integer sums of squares (sum v^2 <= n^2 < 2^63); ApEn
+ *     leaves as its two histograms (index order matters for the FP sum done by the tail kernel).
+ *
+ * Algorithmic bytes: n/8 per stream per kernel (times the slice count for H > 15).
+ */
+#include "common.cuh"
+
+#define PAT_THREADS 256
+
+/* 32 bits starting at cyclic bit position pos (0 <= pos < n + 64), stream length n bits */
+__device__ __forceinline__ uint32_t cyc32(const uint32_t *__restrict__ w, int64_t pos, int64_t n)
+{
+	if (pos + 32 <= n)
+		return get32(w, pos);
+	if (pos >= n)
+		return get32(w, pos - n);	/* n >= 64 guaranteed by the callers' test preconditions */
+	int k = (int) (n - pos);		/* 1..31 bits left before the wrap */
+	return (get32(w, pos) & mask_below((uint32_t) k)) | (get32(w, 0) >> k);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(PAT_THREADS)
+nonoverlapping_kernel(DevParams P, const uint32_t *__restrict__ in, const uint32_t *__restrict__ tmpl,
+		      uint32_t *__restrict__ wout)
+{
+	extern __shared__ uint32_t hist[];
+	const int64_t s = blockIdx.x;
+	const int blk = blockIdx.y;
+	const int m = P.nonov_m;
+	const int bins = 1 << m;
+	for (int i = threadIdx.x; i < bins; i += PAT_THREADS)
+		hist[i] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t M = P.nonov_M, start = (int64_t) blk * M;
+	const int64_t last = M - m;				/* last window start inside the block */
+	const int64_t groups = (last >> 5) + 1;
+	for (int64_t g = threadIdx.x; g < groups; g += PAT_THREADS) {
+		const int64_t j0 = g * 32;
+		uint32_t cur = get32(w, start + j0), nxt = get32(w, start + j0 + 32);
+		int cnt = (last - j0 >= 31) ? 32 : (int) (last - j0 + 1);
+#pragma unroll 8
+		for (int p = 0; p < 32; p++) {
+			if (p < cnt) {
+				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - m);
+				atomicAdd(&hist[v], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	uint32_t *__restrict__ o = wout + s * P.nw;
+	for (int t = threadIdx.x; t < P.ntemplates; t += PAT_THREADS)
+		o[t * 8 + blk] = hist[__ldg(tmpl + t)];
+}
+
+cudaError_t launch_nonoverlapping(const DevParams &P, const LaunchCtx &L, const uint32_t *d_templates)
+{
+	if (!(P.enabled & (1u << STSGPU_TEST_NON_OVERLAPPING)))
+		return cudaSuccess;
+	size_t smem = (size_t) sizeof(uint32_t) << P.nonov_m;
+	cudaError_t e = cudaFuncSetAttribute(nonoverlapping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (e != cudaSuccess)
+		return e;
+	dim3 grid((unsigned) L.nstreams, 8);
+	nonoverlapping_kernel<<<grid, PAT_THREADS, smem, L.stream>>>(P, L.d_in, d_templates, L.d_w);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* block-wide sum of unsigned 64-bit values; result valid in thread 0 */
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *scratch)
+{
+	v = (unsigned long long) warp_sum_ll((long long) v);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0)
+		scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	unsigned long long t = 0;
+	if (threadIdx.x == 0)
+		for (int i = 0; i < PAT_THREADS / 32; i++)
+			t += scratch[i];
+	return t;
+}
+
+/*
+ * apen_hist layout per stream: [2^(apen_m+1) bins of level apen_m+1][2^apen_m bins of level apen_m]
+ */
+__global__ void __launch_bounds__(PAT_THREADS)
+cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
+		   uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ debug_hist, int debug_bits)
+{
+	extern __shared__ uint32_t hist[];
+	__shared__ unsigned long long red[PAT_THREADS / 32];
+	const int64_t s = blockIdx.x;
+	const uint32_t slice = blockIdx.y;
+	const int H = debug_hist ? debug_bits : P.hist_bits;
+	const int sb = debug_hist ? (H > 15 ? H - 15 : 0) : P.hist_slice_bits;
+	const int B = H - sb;					/* local histogram bits */
+	const uint32_t lmask = (1u << B) - 1u;
+	for (int i = threadIdx.x; i < (1 << B); i += PAT_THREADS)
+		hist[i] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t n = P.n;
+	const int64_t groups = (n + 31) >> 5;
+	for (int64_t g = threadIdx.x; g < groups; g += PAT_THREADS) {
+		const int64_t j0 = g * 32;
+		uint32_t cur, nxt;
+		if (j0 + 64 <= n) {
+			cur = ldw(w, g);
+			nxt = ldw(w, g + 1);
+		} else {
+			cur = cyc32(w, j0, n);
+			nxt = cyc32(w, j0 + 32, n);
+		}
+		int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
+#pragma unroll 8
+		for (int p = 0; p < 32; p++) {
+			if (p < cnt) {
+				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
+				if ((v >> B) == slice)
+					atomicAdd(&hist[v & lmask], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	if (debug_hist) {
+		uint32_t *o = debug_hist + ((size_t) slice << B);
+		for (int i = threadIdx.x; i < (1 << B); i += PAT_THREADS)
+			o[i] = hist[i];
+		return;
+	}
+
+	const int sm = (P.enabled & (1u << STSGPU_TEST_SERIAL)) ? P.serial_m : -100;
+	const int am = (P.enabled & (1u << STSGPU_TEST_APEN)) ? P.apen_m : -100;
+	int lowest = H;
+	if (sm > 0) lowest = min(lowest, max(sm - 2, 1));
+	if (am > 0) lowest = min(lowest, am);
+	long long *o = st + s * P.nst;
+	for (int lvl = H; lvl >= lowest; lvl--) {
+		const int b = lvl - sb;			/* local bits at this level (>= 0 by construction) */
+		const int nb = 1 << b;
+		const bool is_serial = (lvl == sm || lvl == sm - 1 || lvl == sm - 2);
+		const bool is_apen = (lvl == am + 1 || lvl == am);
+		if (is_serial || is_apen) {
+			unsigned long long sq = 0, lin = 0;
+			const unsigned long long base = (unsigned long long) slice << b;
+			for (int i = threadIdx.x; i < nb; i += PAT_THREADS) {
+				unsigned long long c = hist[i];
+				sq += c * c;
+				lin += (base + i) * c;
+			}
+			sq = block_sum_u64(sq, red);
+			if (is_apen)
+				lin = block_sum_u64(lin, red);
+			if (threadIdx.x == 0) {
+				if (is_serial)
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_SERIAL] + (sm - lvl)), sq);
+				if (is_apen) {
+					int r = lvl - am;	/* 1: level m+1, 0: level m */
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_APEN] + 2 + r), sq);
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_APEN] + 4 + r), lin);
+				}
+			}
+			if (is_apen) {
+				uint32_t *dst = apen_hist + s * ((size_t) 3 << am) + (lvl == am + 1 ? 0 : ((size_t) 2 << am))
+						+ ((size_t) slice << b);
+				for (int i = threadIdx.x; i < nb; i += PAT_THREADS)
+					dst[i] = hist[i];
+			}
+		}
+		if (lvl == lowest)
+			break;
+		/* fold to the next level in place: new[i] = old[2i] + old[2i+1] */
+		const int half = nb >> 1;
+		for (int c0 = 0; c0 < max(half, 1); c0 += PAT_THREADS) {
+			int i = c0 + threadIdx.x;
+			uint32_t v = 0;
+			if (i < half)
+				v = hist[2 * i] + hist[2 * i + 1];
+			__syncthreads();
+			if (i < half)
+				hist[i] = v;
+			__syncthreads();
+		}
+	}
+}
+
+cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist)
+{
+	if (!(P.enabled & ((1u << STSGPU_TEST_SERIAL) | (1u << STSGPU_TEST_APEN))))
+		return cudaSuccess;
+	const int B = P.hist_bits - P.hist_slice_bits;
+	size_t smem = (size_t) sizeof(uint32_t) << B;
+	cudaError_t e = cudaFuncSetAttribute(cyclic_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e != cudaSuccess)
+		return e;
+	dim3 grid((unsigned) L.nstreams, 1u << P.hist_slice_bits);
+	cyclic_hist_kernel<<<grid, PAT_THREADS, smem, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, nullptr, 0);
+	return cudaGetLastError();
+}
+
+/* parity helper: full cyclic histogram of one stream at `bits` into d_out (2^bits counters) */
+cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits,
+				   uint32_t *d_out)
+{
+	const int sb = bits > 15 ? bits - 15 : 0;
+	size_t smem = (size_t) sizeof(uint32_t) << (bits - sb);
+	cudaError_t e = cudaFuncSetAttribute(cyclic_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e != cudaSuccess)
+		return e;
+	dim3 grid(1, 1u << sb);
+	cyclic_hist_kernel<<<grid, PAT_THREADS, smem, L.stream>>>(P, L.d_in + stream_index * P.pitch_words, nullptr,
+								  nullptr, d_out, bits);
+	return cudaGetLastError();
+}

@@ -1,0 +1,374 @@
+/*
+ * k_tails.cu - the floating point tails: integer statistics -> p-values.
+ *
+ * COMPILED WITH -fmad=false: every expression below is written in the reference's operand order
+ * and must round like gcc -std=c99 rounds it on x86-64 (no FMA contraction), so that the only
+ * difference left against the reference is CUDA's libdevice vs glibc in erf/erfc/exp/log (<= 2 ulp).
+ * lgamma(a) is only ever needed for per-configuration constants a, so the host evaluates it with
+ * glibc (as the reference does through cephes.h:33-35) and passes the values in TailConsts.
+ *
+ * One CTA per stream.
+ *   stage 1: one thread per p-value slot (all tests except CumulativeSums and ApproximateEntropy);
+ *   stage 2: CumulativeSums (cusum.c:329-370): warps 0/1 evaluate 32 terms of the two series at a
+ *            time and add them in the reference's k order;
+ *   stage 3: ApproximateEntropy phi (approximateEntropy.c:396-407): the CTA evaluates
+ *            C*log(C/n) for 1024 bins at a time, thread 0 adds them in index order.
+ */
+#include "common.cuh"
+#include "tails.h"
+
+#define TAIL_THREADS 256
+#define NONP STSGPU_NON_P_VALUE
+
+/* utils/cephes.c:31-32,49-50 */
+#define K_MACHEP 1.11022302462515654042363e-16
+#define K_MAXLOG 7.0978271289338399673222e2
+#define K_BIG 4.503599627370496e15
+#define K_BIGINV 2.22044604925031308085e-16
+#define K_SQRT2 1.41421356237309504880
+
+__device__ double d_igam_series(double a, double x, double lga);
+
+/* utils/cephes.c:60-132 */
+__device__ double d_igamc(double a, double x, double lga)
+{
+	if ((x <= 0) || (a <= 0))
+		return 1.0;
+	if ((x < 1.0) || (x < a))
+		return 1.e0 - d_igam_series(a, x, lga);	/* igam's own redirect (x > 1 && x > a) cannot trigger here */
+	double ax = a * log(x) - x - lga;
+	if (ax < -K_MAXLOG)
+		return 0.0;
+	ax = exp(ax);
+	double y = 1.0 - a;
+	double z = x + y + 1.0;
+	double c = 0.0;
+	double pkm2 = 1.0;
+	double qkm2 = x;
+	double pkm1 = x + 1.0;
+	double qkm1 = z * x;
+	double ans = pkm1 / qkm1;
+	double t;
+	do {
+		c += 1.0;
+		y += 1.0;
+		z += 2.0;
+		double yc = y * c;
+		double pk = pkm1 * z - pkm2 * yc;
+		double qk = qkm1 * z - qkm2 * yc;
+		if (qk != 0) {
+			double r = pk / qk;
+			t = fabs((ans - r) / r);
+			ans = r;
+		} else {
+			t = 1.0;
+		}
+		pkm2 = pkm1;
+		pkm1 = pk;
+		qkm2 = qkm1;
+		qkm1 = qk;
+		if (fabs(pk) > K_BIG) {
+			pkm2 *= K_BIGINV;
+			pkm1 *= K_BIGINV;
+			qkm2 *= K_BIGINV;
+			qkm1 *= K_BIGINV;
+		}
+	} while (t > K_MACHEP);
+	return ans * ax;
+}
+
+/* utils/cephes.c:135-174, power series branch (reached only with x < 1 or x < a, so no recursion) */
+__device__ double d_igam_series(double a, double x, double lga)
+{
+	if ((x <= 0) || (a <= 0))
+		return 0.0;
+	double ax = a * log(x) - x - lga;
+	if (ax < -K_MAXLOG)
+		return 0.0;
+	ax = exp(ax);
+	double r = a;
+	double c = 1.0;
+	double ans = 1.0;
+	do {
+		r += 1.0;
+		c *= x / r;
+		ans += c;
+	} while (c / ans > K_MACHEP);
+	return ans * ax / a;
+}
+
+/* utils/cephes.c:416-430 */
+__device__ __forceinline__ double d_normal(double x)
+{
+	if (x > 0)
+		return 0.5 * (1 + erf(x / K_SQRT2));
+	return 0.5 * (1 - erf(-x / K_SQRT2));
+}
+
+__device__ __forceinline__ int test_of_slot(const DevParams &P, int q, int *sub)
+{
+	int t = 0;
+	for (int k = 1; k <= 15; k++)
+		if ((P.enabled >> k) & 1u)
+			if (P.pv_off[k] <= q)
+				t = k;
+	*sub = q - P.pv_off[t];
+	return t;
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+tails_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ w_all,
+	     const uint32_t *__restrict__ apen_hist, double *__restrict__ pv_all, int64_t nstreams)
+{
+	__shared__ double terms[1024];
+	const int64_t s = blockIdx.x;
+	if (s >= nstreams)
+		return;
+	long long *st = st_all + s * P.nst;
+	const uint32_t *wc = w_all + s * P.nw;
+	double *pv = pv_all + s * P.npv;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const long long n = P.n;
+
+	/* ---------------- stage 1 ---------------- */
+	for (int q = tid; q < P.npv; q += TAIL_THREADS) {
+		int sub;
+		const int t = test_of_slot(P, q, &sub);
+		const long long *c = st + P.st_off[t];
+		double p = 0.0;
+		bool write = true;
+		switch (t) {
+		case STSGPU_TEST_FREQUENCY: {			/* frequency.c:206-212 */
+			double s_obs = fabs((double) c[0]) / K.sqrtn;
+			double f = s_obs / K.sqrt2;
+			p = erfc(f);
+			break;
+		}
+		case STSGPU_TEST_BLOCK_FREQUENCY: {		/* blockFrequency.c:217-247 */
+			const long long M = P.bf_M, N = P.bf_N;
+			double sum = 0.0;
+			for (long long i = 0; i < N; i++) {
+				double pi = (double) c[1 + i] / (double) M;
+				double v = pi - 0.5;
+				sum += v * v;
+			}
+			double chi_squared = 4.0 * M * sum;
+			p = d_igamc(N / 2.0, chi_squared / 2.0, K.lgam_bf);
+			break;
+		}
+		case STSGPU_TEST_RUNS: {			/* runs.c:219-246 */
+			double pi = (double) c[0] / (double) n;
+			bool possible = (fabs(pi - 0.5) >= K.two_over_sqrtn) ? false : true;
+			st[P.st_off[t] + 2] = possible ? 1 : 0;
+			if (possible) {
+				long long V_n = c[1];
+				double erfc_arg = fabs(V_n - 2.0 * (double) n * pi * (1.0 - pi)) /
+						  (2.0 * pi * (1.0 - pi) * K.sqrt2n);
+				p = erfc(erfc_arg);
+			} else {
+				p = NONP;
+			}
+			break;
+		}
+		case STSGPU_TEST_LONGEST_RUN: {			/* longestRunOfOnes.c:411-421 */
+			const long long N = P.lr_N;
+			double chi2 = 0.0;
+			for (int i = 0; i <= 6; i++) {
+				double chi_term = c[i] - (N * K.lr_pi[i]);
+				chi2 += chi_term * chi_term / (N * K.lr_pi[i]);
+			}
+			p = d_igamc(6 / 2.0, chi2 / 2.0, K.lgam_3);
+			break;
+		}
+		case STSGPU_TEST_RANK: {			/* rank.c:322-341 */
+			const long long mc = P.rank_count, F_M = c[0], F_M1 = c[1];
+			const long long F_rem = mc - (F_M + F_M1);
+			st[P.st_off[t] + 2] = F_rem;
+			double chi = (((F_M - mc * K.p_32) * (F_M - mc * K.p_32) / (mc * K.p_32)) +
+				      ((F_M1 - mc * K.p_31) * (F_M1 - mc * K.p_31) / (mc * K.p_31)) +
+				      ((F_rem - mc * K.p_30) * (F_rem - mc * K.p_30) / (mc * K.p_30)));
+			p = exp(-chi / 2.0);
+			break;
+		}
+		case STSGPU_TEST_DFT: {				/* discreteFourierTransform.c:401-423 */
+			double N_0 = (double) 0.95 * n / 2.0;
+			double d = (c[0] - N_0) / K.sqrtn4_095_005;
+			p = erfc(fabs(d) / K.sqrt2);
+			break;
+		}
+		case STSGPU_TEST_NON_OVERLAPPING: {		/* nonOverlappingTemplateMatchings.c:556-568 */
+			double chi2 = 0.0;
+			for (int i = 0; i < 8; i++) {
+				double chi2_term = ((double) wc[sub * 8 + i] - K.nonov_mu) / K.nonov_sqrt_sigma2;
+				chi2 += (chi2_term * chi2_term);
+			}
+			p = d_igamc(8 / 2.0, chi2 / 2.0, K.lgam_4);
+			break;
+		}
+		case STSGPU_TEST_OVERLAPPING: {			/* overlappingTemplateMatchings.c:290-303 */
+			const long long N = P.ov_N;
+			double chi2 = 0.0;
+			for (int i = 0; i < 6; i++) {
+				double chi2_term = (double) c[i] - (double) N * K.ov_pi[i];
+				chi2 += chi2_term * chi2_term / ((double) N * K.ov_pi[i]);
+			}
+			p = d_igamc(5 / 2.0, chi2 / 2.0, K.lgam_2_5);
+			break;
+		}
+		case STSGPU_TEST_UNIVERSAL: {			/* universal.c:380-390 */
+			double sum = __longlong_as_double(c[0]);
+			double f_n = (sum / (double) P.univ_K);
+			double arg = fabs(f_n - K.univ_expected) / (K.sqrt2 * K.univ_sigma);
+			p = erfc(arg);
+			break;
+		}
+		case STSGPU_TEST_RND_EXCURSION: {		/* randomExcursions.c:358, :470-503, :597-600 */
+			const long long J = c[0];
+			if (J < P.min_zero_crossings) {
+				p = NONP;
+			} else {
+				int x = (sub < 4) ? (sub - 4) : (sub - 3);
+				int ax = x < 0 ? -x : x;
+				double chi2 = 0.0;
+				for (int j = 0; j < 6; j++) {
+					double sum_term = (double) c[1 + 8 * j + sub] - ((double) J * K.rex_pi[ax - 1][j]);
+					chi2 += sum_term * sum_term / ((double) J * K.rex_pi[ax - 1][j]);
+				}
+				p = d_igamc((double) (6 - 1) / 2.0, chi2 / 2.0, K.lgam_2_5);
+			}
+			break;
+		}
+		case STSGPU_TEST_RND_EXCURSION_VAR: {		/* randomExcursionsVariant.c:283, :311-313 */
+			const long long J = c[0];
+			if (J < P.min_zero_crossings) {
+				p = NONP;
+			} else {
+				long long x = (sub < 9) ? (sub - 9) : (sub - 8);
+				long long ax = x < 0 ? -x : x;
+				long long diff = c[1 + sub] - J;
+				if (diff < 0) diff = -diff;
+				p = erfc(diff / (sqrt(2.0 * J * (4.0 * ax - 2.0))));
+			}
+			break;
+		}
+		case STSGPU_TEST_SERIAL: {			/* serial.c:205-224, :414-425 */
+			const int m = P.serial_m;
+			double psi[3];
+			for (int r = 0; r < 3; r++) {
+				int b = m - r;
+				if (b <= 0) {
+					psi[r] = 0.0;
+				} else {
+					double sum = (double) c[r];
+					psi[r] = (sum * (double) ((long long) 1 << b) / (double) n) - (double) n;
+				}
+			}
+			double del1 = psi[0] - psi[1];
+			double del2 = psi[0] - 2.0 * psi[1] + psi[2];
+			if (sub == 0)
+				p = d_igamc((double) ((long long) 1 << (m - 1)) / 2.0, del1 / 2.0, K.lgam_serial1);
+			else
+				p = d_igamc((double) ((long long) 1 << (m - 2)) / 2.0, del2 / 2.0, K.lgam_serial2);
+			break;
+		}
+		case STSGPU_TEST_LINEARCOMPLEXITY: {		/* linearComplexity.c:382-390 */
+			const long long N = P.lc_N;
+			double chi2 = 0.0;
+			for (int i = 0; i < 7; i++)
+				chi2 += (c[i] - N * K.lc_pi[i]) * (c[i] - N * K.lc_pi[i]) / (N * K.lc_pi[i]);
+			p = d_igamc(6 / 2.0, chi2 / 2.0, K.lgam_3);
+			break;
+		}
+		default:
+			write = false;		/* CUSUM and APEN: stages 2 and 3 */
+			break;
+		}
+		if (write)
+			pv[q] = p;
+	}
+
+	/* ---------------- stage 2: CumulativeSums, cusum.c:353-369 ---------------- */
+	if ((P.enabled & (1u << STSGPU_TEST_CUSUM)) && warp < 2) {
+		const long long z = st[P.st_off[STSGPU_TEST_CUSUM] + 3 + warp];	/* warp 0: forward, 1: backward */
+		double sum1 = 0.0, sum2 = 0.0;
+		if (z > 0) {
+			const long long k1lo = (-n / z + 1) / 4, k1hi = (n / z - 1) / 4;
+			for (long long k0 = k1lo; k0 <= k1hi; k0 += 32) {
+				long long k = k0 + lane;
+				double a = 0.0, b = 0.0;
+				if (k <= k1hi) {
+					a = d_normal(((4 * k + 1) * z) / K.sqrtn);
+					b = d_normal(((4 * k - 1) * z) / K.sqrtn);
+				}
+#pragma unroll 4
+				for (int l = 0; l < 32; l++) {
+					sum1 += __shfl_sync(0xffffffffu, a, l);
+					sum1 -= __shfl_sync(0xffffffffu, b, l);
+				}
+			}
+			const long long k2lo = (-n / z - 3) / 4, k2hi = (n / z - 1) / 4;
+			for (long long k0 = k2lo; k0 <= k2hi; k0 += 32) {
+				long long k = k0 + lane;
+				double a = 0.0, b = 0.0;
+				if (k <= k2hi) {
+					a = d_normal(((4 * k + 3) * z) / K.sqrtn);
+					b = d_normal(((4 * k + 1) * z) / K.sqrtn);
+				}
+#pragma unroll 4
+				for (int l = 0; l < 32; l++) {
+					sum2 += __shfl_sync(0xffffffffu, a, l);
+					sum2 -= __shfl_sync(0xffffffffu, b, l);
+				}
+			}
+		}
+		if (lane == 0)
+			pv[P.pv_off[STSGPU_TEST_CUSUM] + warp] = 1.0 - sum1 + sum2;
+	}
+
+	/* ---------------- stage 3: ApproximateEntropy ---------------- */
+	if (P.enabled & (1u << STSGPU_TEST_APEN)) {
+		const int m = P.apen_m;
+		const uint32_t *h = apen_hist + s * ((size_t) 3 << m);
+		double phi[2];
+		for (int r = 0; r < 2; r++) {
+			const uint32_t *hr = (r == 1) ? h : h + ((size_t) 2 << m);	/* r = 0: level m, r = 1: level m+1 */
+			const long long bins = 1LL << (m + r);
+			double sum = 0.0;
+			for (long long base = 0; base < bins; base += 1024) {
+				__syncthreads();
+				for (int i = tid; i < 1024; i += TAIL_THREADS) {
+					double term = 0.0;
+					if (base + i < bins) {
+						uint32_t C = hr[base + i];
+						if (C)
+							term = (double) C * log(C / (double) n);
+					}
+					terms[i] = term;
+				}
+				__syncthreads();
+				if (tid == 0) {
+					long long lim = bins - base < 1024 ? bins - base : 1024;
+					for (int i = 0; i < lim; i++)
+						sum += terms[i];
+				}
+			}
+			phi[r] = sum / (double) n;
+		}
+		if (tid == 0) {
+			long long *c = st + P.st_off[STSGPU_TEST_APEN];
+			c[0] = __double_as_longlong(phi[0]);
+			c[1] = __double_as_longlong(phi[1]);
+			double ApEn = phi[0] - phi[1];
+			double chi_squared = 2.0 * n * (K.log2_ - ApEn);
+			pv[P.pv_off[STSGPU_TEST_APEN]] =
+				d_igamc((double) ((long long) 1 << (m - 1)), chi_squared / 2.0, K.lgam_apen);
+		}
+	}
+}
+
+cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist)
+{
+	tails_kernel<<<(unsigned) L.nstreams, TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_w, d_apen_hist, L.d_pv,
+									   L.nstreams);
+	return cudaGetLastError();
+}
