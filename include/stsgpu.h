@@ -214,7 +214,11 @@ int stsgpu_comm_barrier(stsgpu_ctx *ctx);
 
 /* ---- measurement --------------------------------------------------------------------------- */
 
-/* enable per-kernel CUDA-event timing of subsequent submits (adds event records only) */
+/*
+ * Per-kernel-group CUDA events are always recorded on the stream each group is launched on.
+ * on = 1 additionally serialises all groups on one stream, so that each duration is that of the
+ * group running alone (otherwise groups overlap on four streams and durations include sharing).
+ */
 int stsgpu_set_profiling(stsgpu_ctx *ctx, int on);
 /* kernels launched by the last submit; name/ms for entry i (ms valid after stsgpu_wait) */
 int stsgpu_kernel_count(const stsgpu_ctx *ctx);

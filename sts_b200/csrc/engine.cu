@@ -499,8 +499,7 @@ static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 	for (int g = 0; g < G_COUNT; g++) {
 		L.stream = (prof || groups[g].stream < 0) ? sm : ctx->s_aux[groups[g].stream];
 		const int slot = ctx->nkernels;
-		if (prof)
-			CK(cudaEventRecord(ctx->k_ev0[slot], L.stream));
+		CK(cudaEventRecord(ctx->k_ev0[slot], L.stream));
 		cudaError_t e = cudaSuccess;
 		int64_t launched = 0;
 		switch (g) {
@@ -521,11 +520,9 @@ static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 			return STSGPU_E_CUDA;
 		}
 		ctx->launches += launched;
-		if (prof) {
-			CK(cudaEventRecord(ctx->k_ev1[slot], L.stream));
-			ctx->k_name[slot] = groups[g].name;
-			ctx->nkernels++;
-		}
+		CK(cudaEventRecord(ctx->k_ev1[slot], L.stream));
+		ctx->k_name[slot] = groups[g].name;
+		ctx->nkernels++;
 	}
 	if (!prof) {
 		for (int i = 0; i < STS_AUX_STREAMS; i++) {
@@ -536,19 +533,16 @@ static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 	L.stream = sm;
 	{
 		const int slot = ctx->nkernels;
-		if (prof)
-			CK(cudaEventRecord(ctx->k_ev0[slot], sm));
+		CK(cudaEventRecord(ctx->k_ev0[slot], sm));
 		cudaError_t e = launch_tails(P, ctx->K, L, ctx->d_apen_hist);
 		if (e != cudaSuccess) {
 			set_err(ctx, "tails", e);
 			return STSGPU_E_CUDA;
 		}
 		ctx->launches += 1;
-		if (prof) {
-			CK(cudaEventRecord(ctx->k_ev1[slot], sm));
-			ctx->k_name[slot] = "tails(p-values)";
-			ctx->nkernels++;
-		}
+		CK(cudaEventRecord(ctx->k_ev1[slot], sm));
+		ctx->k_name[slot] = "tails(p-values)";
+		ctx->nkernels++;
 	}
 	CK(cudaEventRecord(ctx->ev_end, sm));
 	CK(cudaMemcpyAsync(ctx->h_pv, ctx->d_pv, (size_t) nstreams * lay.npv * sizeof(double), cudaMemcpyDeviceToHost, sm));

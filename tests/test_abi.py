@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library exists, loads without a GPU, exports every symbol include/stsgpu.h declares,
+and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import sts_b200
+from sts_b200 import binding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "stsgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stsgpu_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    binding.build_library()
+    lib = ctypes.CDLL(binding.library_path())
+    declared = header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libstsgpu.so does not export %s" % name
+    assert sorted(binding.EXPORTS) == declared, "binding.EXPORTS out of sync with include/stsgpu.h"
+    assert lib.stsgpu_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # stsgpu_params: 2 x i32, 2 x i64, u32 + i32, i64, 4 x i32, i64  = 64 bytes; layout: 6 + 4*16 int32
+    assert ctypes.sizeof(binding.Params) == 64
+    assert ctypes.sizeof(binding.Layout) == 4 * (6 + 64)
+
+
+def test_default_params_are_the_reference_defaults():
+    p = sts_b200.default_params()
+    assert (p.n, p.block_frequency_M, p.non_overlapping_m, p.overlapping_m, p.apen_m, p.serial_m,
+            p.linear_complexity_M) == (1048576, 16384, 9, 9, 10, 16, 500)      # defs.h:110-125
+    assert p.test_mask == 0xFFFE
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sts_b200.EngineError) as ei:
+        sts_b200.Engine(max_streams=1)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    """only tests/, __graft_entry__.smoke and bench.py's baseline legs may touch oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sts_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("oracle_layout_for", "") or f == "__init__.py", \
+                    "%s mentions the oracle" % os.path.join(dirpath, f)

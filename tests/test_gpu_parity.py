@@ -1,0 +1,221 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI (libstsgpu.so via ctypes), against
+  (1) the golden vectors produced by the unmodified reference binary (tests/golden/*.npz),
+  (2) the CPU oracle on the same seeded inputs, and
+  (3) size-independent properties at BASELINE's full batch size (1024 x 2^20-bit streams).
+
+Bars: integer statistics, template counts, histograms bit-exact; p-values within PV_RTOL = 1e-9 relative
+(the north-star tolerance) - in practice ~1e-15, the residue of CUDA libdevice vs glibc erf/erfc/exp/log.
+CumulativeSums p-values are formed as 1 - sum1 + sum2 (cusum.c:369), so a p-value near 0 carries the
+absolute rounding noise of sums of magnitude 1; for that test only an absolute floor PV_ATOL_CUSUM
+applies on top of the relative bar."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import check_against_golden, golden_cases, golden_input, golden_params, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PV_RTOL = 1e-9
+PV_ATOL_CUSUM = 1e-13
+
+
+@pytest.fixture(scope="module")
+def sts():
+    import sts_b200
+    sts_b200.load_library()          # raises if the CUDA extension is missing: no fallback
+    return sts_b200
+
+
+def engine_for(sts, g, streams, mask=None):
+    prm = golden_params(g)
+    n = prm["n"]
+    m = sts.ALL_TESTS if mask is None else mask
+    if n & (n - 1):
+        m &= ~(1 << 7)               # this build's FFT handles n = 2^k only (out of scope list)
+    return sts.Engine(max_streams=streams, test_mask=m, **prm), m
+
+
+def compare_with_oracle(sts, oracle, eng, mask, prm, raw, streams, pv, st, w):
+    lay = eng.layout
+    opv, ost, ow, olay = oracle.run(oracle.make_params(test_mask=mask, **prm), raw, streams,
+                                    nthreads=os.cpu_count() or 1)
+    assert lay.enabled_mask == olay.enabled_mask
+    assert (lay.npv, lay.nst, lay.nw) == (olay.npv, olay.nst, olay.nw)
+    assert list(lay.pv_off) == list(olay.pv_off) and list(lay.st_off) == list(olay.st_off)
+    assert (w == ow).all(), "W[template][block] differs"
+    fp = {lay.st_off[10]} if (lay.enabled_mask >> 10) & 1 else set()
+    if (lay.enabled_mask >> 11) & 1:
+        fp |= {lay.st_off[11], lay.st_off[11] + 1}
+    cols = [c for c in range(lay.nst) if c not in fp]
+    bad = np.argwhere(st[:, cols] != ost[:, cols])
+    assert bad.size == 0, "integer statistics differ at (stream, slot) %s" % bad[:8].tolist()
+    for c in fp:                     # double bit patterns: Universal sum (bit-exact), ApEn phi (FP)
+        a = st[:, c].copy().view(np.float64)
+        b = ost[:, c].copy().view(np.float64)
+        if c == lay.st_off[10] and (lay.enabled_mask >> 10) & 1:
+            assert (a == b).all(), "Universal sum must be bit-identical (sequential order, host log table)"
+        else:
+            assert rel_err(a, b).max() <= 1e-13
+    for t in range(1, 16):
+        if not (lay.enabled_mask >> t) & 1:
+            continue
+        a = pv[:, lay.pv_off[t]:lay.pv_off[t] + lay.pv_cnt[t]]
+        b = opv[:, olay.pv_off[t]:olay.pv_off[t] + olay.pv_cnt[t]]
+        r = rel_err(a, b)
+        if t == 3:
+            r[np.abs(a - b) <= PV_ATOL_CUSUM] = 0.0
+        assert r.max() <= PV_RTOL, "test %d (%s): p-value rel err %.3g" % (t, sts.TEST_NAMES[t], r.max())
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases() if "config4" not in c])
+def test_engine_matches_reference_golden_and_oracle(sts, oracle, case):
+    g = load_golden(case)
+    streams = int(g["streams"])
+    raw = golden_input(g, oracle)
+    eng, mask = engine_for(sts, g, streams)
+    with eng:
+        pv, st, w = eng.run(raw, streams)
+        lay = eng.layout
+        gg = {k: g[k] for k in g.files}
+        gg["enabled_mask"] = np.int64(int(g["enabled_mask"]) & mask)
+        bad = check_against_golden(gg, pv, st, w, lay, pv_rtol=PV_RTOL)
+        # cusum absolute floor (see module docstring)
+        bad = [b for b in bad if not b.startswith("test 3:")] + \
+              [b for b in bad if b.startswith("test 3:") and
+               np.abs(pv[:, lay.pv_off[3]:lay.pv_off[3] + 2] - g["pv_3"]).max() > PV_ATOL_CUSUM]
+        assert not bad, "\n".join(bad)
+        compare_with_oracle(sts, oracle, eng, mask, golden_params(g), raw, streams, pv, st, w)
+
+
+def test_engine_config4_parameters(sts, oracle):
+    """BASELINE config 4: n = 10^7, LC M = 5000 (the `1 << M` class rule), template m = 10, Serial/ApEn
+    m = 16 (two histogram slices of 2^16 counters each, 3 * 2^16 ApEn bins summed in index order)."""
+    if "lcg_config4_2" not in golden_cases():
+        pytest.skip("config-4 golden not generated")
+    g = load_golden("lcg_config4_2")
+    raw = golden_input(g, oracle)
+    eng, mask = engine_for(sts, g, 2)
+    with eng:
+        pv, st, w = eng.run(raw, 2)
+        lay = eng.layout
+        assert not (lay.enabled_mask >> 2) & 1      # BlockFrequency self-disables (blockFrequency.c:119)
+        gg = {k: g[k] for k in g.files}
+        gg["enabled_mask"] = np.int64(int(g["enabled_mask"]) & mask)
+        bad = check_against_golden(gg, pv, st, w, lay, pv_rtol=PV_RTOL)
+        assert not bad, "\n".join(bad)
+
+
+def test_device_lcg_is_the_reference_generator(sts, oracle):
+    with sts.Engine(max_streams=8) as eng:
+        eng.generate_lcg(0, 8)
+        assert (eng.download_input(8) == oracle.lcg_bytes(0, 8)).all()
+        eng.generate_lcg(1000, 4)                    # skip-ahead: golden case lcg_default_off1000_4
+        assert (eng.download_input(4) == oracle.lcg_bytes(1000, 4)).all()
+    with sts.Engine(max_streams=2, n=1000008, test_mask=sts.ALL_TESTS & ~(1 << 7)) as eng:
+        eng.generate_lcg(1, 2)                       # ragged stream length, mid-file start
+        assert (eng.download_input(2) == oracle.lcg_bytes(1, 2, 1000008)).all()
+
+
+@pytest.mark.parametrize("bits", [3, 9, 11, 16, 18])
+def test_cyclic_pattern_histogram(sts, oracle, bits):
+    raw = oracle.lcg_bytes(3, 1)
+    with sts.Engine(max_streams=1) as eng:
+        eng.upload(raw, 1)
+        h = eng.debug_pattern_histogram(0, bits)
+    assert (h == oracle.pattern_histogram(raw, 1 << 20, bits)).all()
+    assert int(h.sum()) == 1 << 20
+
+
+def test_full_batch_properties_and_sampled_parity(sts, oracle):
+    """BASELINE config 2: 1024 streams.  Properties that hold for any input + oracle parity on a sample."""
+    B = 1024
+    n = 1 << 20
+    with sts.Engine(max_streams=B) as eng:
+        eng.generate_lcg(0, B)
+        eng.submit_resident(B, 0)
+        eng.wait()
+        pv, st, w = eng.results()
+        lay = eng.layout
+        o = lay.st_off
+        ones = st[:, o[4]]
+        assert (st[:, o[1]] == 2 * ones - n).all()                         # S_n = #1 - #0
+        assert (st[:, o[2]] == 64).all() and (st[:, o[2] + 1:o[2] + 65].sum(1) == ones).all()
+        assert (st[:, o[3]] == st[:, o[1]]).all()                          # cusum final S
+        assert (st[:, o[3] + 1] >= np.maximum(st[:, o[3]], 0)).all() and (st[:, o[3] + 2] <= 0).all()
+        assert (st[:, o[5]:o[5] + 7].sum(1) == 104).all()                  # longest-run blocks
+        assert (st[:, o[6]:o[6] + 3].sum(1) == 1024).all()                 # matrices
+        assert ((st[:, o[7]] > 0) & (st[:, o[7]] <= n // 2)).all()
+        assert (st[:, o[9]:o[9] + 6].sum(1) == 1016).all()                 # overlapping blocks
+        J = st[:, o[12]]
+        v = st[:, o[12] + 1:o[12] + 49].reshape(B, 6, 8)
+        assert (v.sum(1) == J[:, None]).all()                              # every cycle lands in one class per state
+        assert (st[:, o[13]] == J).all()
+        assert (st[:, o[14]] >= n * n // 65536).all()                      # sum v^2 >= n^2 / bins
+        assert (st[:, o[15]:o[15] + 7].sum(1) == 2097).all()               # LC blocks
+        # template counts: every block's windows are counted at most once per template
+        assert (w.reshape(B, 148, 8).sum(1) <= 131072 - 8).all()
+        # p-values are in [0, 1] or NON_P_VALUE
+        okp = ((pv >= 0) & (pv <= 1.0 + 1e-12)) | (pv == sts.NON_P_VALUE)
+        assert okp.all()
+        # determinism / idempotence
+        eng.submit_resident(B, 0)
+        eng.wait()
+        pv2, st2, w2 = eng.results()
+        assert (pv2 == pv).all() and (st2 == st).all() and (w2 == w).all()
+        raw = eng.download_input(B)
+    # batch-split invariance: streams 512..575 alone give the same records
+    with sts.Engine(max_streams=64) as eng:
+        p64, s64, w64 = eng.run(raw[512 * n // 8:576 * n // 8].copy(), 64, 512)
+        assert (p64 == pv[512:576]).all() and (s64 == st[512:576]).all() and (w64 == w[512:576]).all()
+    # oracle parity on 16 streams spread over the batch
+    idx = np.linspace(0, B - 1, 16).astype(int)
+    sub = np.concatenate([raw[i * n // 8:(i + 1) * n // 8] for i in idx])
+    opv, ost, ow, olay = oracle.run(oracle.make_params(), sub, len(idx), nthreads=os.cpu_count() or 1)
+    assert (ow == w[idx]).all()
+    fp = [lay.st_off[11], lay.st_off[11] + 1]
+    cols = [c for c in range(lay.nst) if c not in fp]
+    assert (ost[:, cols] == st[idx][:, cols]).all()
+    r = rel_err(pv[idx], opv)
+    c3 = slice(lay.pv_off[3], lay.pv_off[3] + 2)
+    r[:, c3][np.abs(pv[idx][:, c3] - opv[:, c3]) <= PV_ATOL_CUSUM] = 0.0
+    assert r.max() <= PV_RTOL
+
+
+def test_partial_test_masks(sts, oracle):
+    """state->testVector subsets (the reference's -t flag) change the record layout, not the values"""
+    raw = oracle.lcg_bytes(5, 2)
+    with sts.Engine(max_streams=2) as full:
+        pv_all, st_all, w_all = full.run(raw, 2)
+        lay_all = full.layout
+        for mask in (1 << 1, (1 << 8) | (1 << 15), (1 << 7) | (1 << 11) | (1 << 14), (1 << 12), (1 << 13) | (1 << 3)):
+            with sts.Engine(max_streams=2, test_mask=mask) as eng:
+                pv, st, w = eng.run(raw, 2)
+                lay = eng.layout
+                assert lay.enabled_mask == mask
+                for t in range(1, 16):
+                    if (mask >> t) & 1:
+                        a = pv[:, lay.pv_off[t]:lay.pv_off[t] + lay.pv_cnt[t]]
+                        b = pv_all[:, lay_all.pv_off[t]:lay_all.pv_off[t] + lay_all.pv_cnt[t]]
+                        assert (a == b).all(), "test %d differs when run alone" % t
+
+
+def test_error_behaviour(sts):
+    with pytest.raises(sts.EngineError):
+        sts.Engine(max_streams=1, n=1001)                    # n % 8 != 0  (parse_args.c:939)
+    with pytest.raises(sts.EngineError):
+        sts.Engine(max_streams=1, n=10 ** 7)                 # DFT at non power-of-two n: unsupported, said loudly
+    with sts.Engine(max_streams=2) as eng:
+        with pytest.raises(sts.EngineError):
+            eng.wait()                                       # wait without submit
+        with pytest.raises(sts.EngineError):
+            eng.submit_resident(3, 0)                        # over capacity
+        eng.generate_lcg(0, 2)
+        eng.submit_resident(2, 0)
+        with pytest.raises(sts.EngineError):
+            eng.submit_resident(2, 0)                        # batch still in flight
+        eng.wait()
+    # small n: tests self-disable exactly like the X_init checks
+    with sts.Engine(max_streams=1, n=2048, test_mask=sts.ALL_TESTS) as eng:
+        assert eng.layout.enabled_mask == (1 << 1) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 7) | (1 << 8) | (1 << 14)
