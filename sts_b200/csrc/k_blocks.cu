@@ -165,11 +165,11 @@ overlapping_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 
 cudaError_t launch_blocks(const DevParams &P, const LaunchCtx &L)
 {
-	if (P.enabled & (1u << STSGPU_TEST_BLOCK_FREQUENCY)) {
+	if ((P.enabled & (1u << STSGPU_TEST_BLOCK_FREQUENCY)) && P.bf_N > 0) {	/* N = 0: slot 0 stays 0 */
 		dim3 grid((unsigned) L.nstreams, (unsigned) ((P.bf_N + BLK_WARPS - 1) / BLK_WARPS));
 		block_frequency_kernel<<<grid, BLK_WARPS * 32, 0, L.stream>>>(P, L.d_in, L.d_st);
 	}
-	if (P.enabled & (1u << STSGPU_TEST_LONGEST_RUN)) {
+	if ((P.enabled & (1u << STSGPU_TEST_LONGEST_RUN)) && P.lr_N > 0) {
 		int64_t gy = (P.lr_N + BLK_WARPS - 1) / BLK_WARPS;
 		if (gy > 16) gy = 16;
 		if (gy < 1) gy = 1;

@@ -216,6 +216,17 @@ def test_error_behaviour(sts):
         with pytest.raises(sts.EngineError):
             eng.submit_resident(2, 0)                        # batch still in flight
         eng.wait()
-    # small n: tests self-disable exactly like the X_init checks
-    with sts.Engine(max_streams=1, n=2048, test_mask=sts.ALL_TESTS) as eng:
-        assert eng.layout.enabled_mask == (1 << 1) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 7) | (1 << 8) | (1 << 14)
+
+
+@pytest.mark.parametrize("n", [2048, 65536, 1 << 17, 400000])
+def test_small_streams_against_oracle(sts, oracle, n):
+    """short streams: most tests self-disable exactly like the X_init checks; the rest must still agree"""
+    streams = 3
+    raw = oracle.lcg_bytes(2, streams, n)
+    mask = sts.ALL_TESTS if n & (n - 1) == 0 else sts.ALL_TESTS & ~(1 << 7)
+    prm = dict(n=n, block_frequency_M=16384, non_overlapping_m=9, overlapping_m=9, apen_m=10, serial_m=16,
+               linear_complexity_M=500)
+    with sts.Engine(max_streams=streams, test_mask=mask, **prm) as eng:
+        assert eng.layout.enabled_mask == oracle.layout(oracle.make_params(test_mask=mask, **prm)).enabled_mask
+        pv, st, w = eng.run(raw, streams)
+        compare_with_oracle(sts, oracle, eng, mask, prm, raw, streams, pv, st, w)
