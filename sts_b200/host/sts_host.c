@@ -1,0 +1,354 @@
+/*
+ * sts_host.c - batching loop and record keeping above the C ABI (see sts_host.h for the mapping to
+ * the reference's functions).  Plain C99, pthread-free on the result path: records are appended in
+ * iteration order by one thread, which removes the races the reference tolerates (runs.c:297,
+ * serial.c:229-249) without changing any p_val content.
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include "sts_host.h"
+
+const char *const sts_testNames[STS_NUMOFTESTS + 1] = {	/* parse_args.c:170-187 */
+	"((all_tests))", "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "LongestRun", "Rank", "DFT",
+	"NonOverlappingTemplate", "OverlappingTemplate", "Universal", "ApproximateEntropy", "RandomExcursions",
+	"RandomExcursionsVariant", "Serial", "LinearComplexity",
+};
+
+void
+sts_err(int exitcode, const char *name, const char *fmt, ...)
+{
+	va_list ap;
+	fflush(stdout);
+	fprintf(stderr, "FATAL error in %s(): ", name);
+	va_start(ap, fmt);
+	vfprintf(stderr, fmt, ap);
+	va_end(ap);
+	fputc('\n', stderr);
+	exit(exitcode);
+}
+
+void
+sts_defaultstate(struct sts_state *s)
+{
+	memset(s, 0, sizeof(*s));
+	s->tp.blockFrequencyBlockLength = 16384;	/* defs.h:110-125 */
+	s->tp.nonOverlappingTemplateLength = 9;
+	s->tp.overlappingTemplateLength = 9;
+	s->tp.approximateEntropyBlockLength = 10;
+	s->tp.serialBlockLength = 16;
+	s->tp.linearComplexitySequenceLength = 500;
+	s->tp.numOfBitStreams = 1;
+	s->tp.uniformityBins = 10;
+	s->tp.n = 1048576;
+	s->tp.uniformityLevel = 0.0001;
+	s->tp.alpha = 0.01;
+	s->runMode = STS_MODE_ITERATE_AND_ASSESS;
+	s->dataFormat = STS_FORMAT_RAW_BINARY;
+	s->numberOfThreads = 1;
+	s->batchStreams = 1024;
+	s->workDir = strdup(".");
+}
+
+/* parse_args.c:960-1013 */
+void
+sts_change_params(struct sts_state *s, long num, long value, double d_value)
+{
+	switch (num) {
+	case 1: s->tp.blockFrequencyBlockLength = value; break;
+	case 2: s->tp.nonOverlappingTemplateLength = value; break;
+	case 3: s->tp.overlappingTemplateLength = value; break;
+	case 4: s->tp.approximateEntropyBlockLength = value; break;
+	case 5: s->tp.serialBlockLength = value; break;
+	case 6: s->tp.linearComplexitySequenceLength = value; break;
+	case 7: s->tp.numOfBitStreams = value; break;
+	case 8: s->tp.uniformityBins = value; break;
+	case 9: s->tp.n = value; break;
+	case 10: s->tp.uniformityLevel = d_value; break;
+	case 11: s->tp.alpha = d_value; break;
+	default: sts_err(3, __func__, "invalid parameter option: %ld", num);
+	}
+}
+
+static void
+pv_append(struct sts_pvals *a, double v)
+{
+	if (a->count == a->cap) {
+		long ncap = a->cap ? a->cap * 2 : 1024;
+		double *nv = realloc(a->v, (size_t) ncap * sizeof(double));
+		if (nv == NULL)
+			sts_err(61, __func__, "cannot grow p-value array to %ld doubles", ncap);
+		a->v = nv;
+		a->cap = ncap;
+	}
+	a->v[a->count++] = v;
+}
+
+/*
+ * init(): the reference runs X_init for tests 1..15 (driver.c:326-330), each of which may disable
+ * itself; here stsgpu_create applies the same rules and reports them through the layout.
+ */
+void
+sts_init(struct sts_state *s)
+{
+	stsgpu_params p;
+	stsgpu_default_params(&p);
+	p.device = s->device;
+	p.n = s->tp.n;
+	p.max_streams = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
+	if (p.max_streams < 1)
+		p.max_streams = 1;
+	p.test_mask = 0;
+	for (int t = 1; t <= STS_NUMOFTESTS; t++)
+		if (s->testVector[t])
+			p.test_mask |= 1u << t;
+	p.block_frequency_M = s->tp.blockFrequencyBlockLength;
+	p.non_overlapping_m = (int32_t) s->tp.nonOverlappingTemplateLength;
+	p.overlapping_m = (int32_t) s->tp.overlappingTemplateLength;
+	p.apen_m = (int32_t) s->tp.approximateEntropyBlockLength;
+	p.serial_m = (int32_t) s->tp.serialBlockLength;
+	p.linear_complexity_M = s->tp.linearComplexitySequenceLength;
+	if ((s->tp.n % 8) != 0)					/* parse_args.c:939 */
+		sts_err(1, __func__, "bitcount(n): %ld must be a multiple of 8", s->tp.n);
+	int rc = stsgpu_create(&p, &s->engine);
+	if (rc != STSGPU_OK)		/* no CPU fallback: fatal, like every error in the reference */
+		sts_err(50, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(NULL));
+	stsgpu_get_layout(s->engine, &s->layout);
+	for (int t = 1; t <= STS_NUMOFTESTS; t++) {
+		bool on = (s->layout.enabled_mask >> t) & 1u;
+		if (s->testVector[t] && !on)
+			fprintf(stderr, "Warning: disabling test %s[%d]: preconditions on n / parameters not met\n",
+				sts_testNames[t], t);
+		s->testVector[t] = on;
+		s->partitionCount[t] = on ? s->layout.pv_cnt[t] : 0;
+	}
+	struct stat st;
+	if (stat(s->workDir, &st) != 0 && mkdir(s->workDir, 0777) != 0)
+		sts_err(50, __func__, "cannot create workDir %s: %s", s->workDir, strerror(errno));
+}
+
+/*
+ * R1, the record-keeping tail every reference X_iterate ends with (frequency.c:218-260 and its 16
+ * copies): classify each p-value against alpha, bump the counters, append to p_val[test].
+ * One generic body serves the 15 table entries because the arithmetic already happened on the GPU.
+ */
+static void
+record_test(struct sts_thread_state *ts, int t)
+{
+	struct sts_state *s = ts->global_state;
+	if (s->testVector[t] != true)
+		return;
+	if (ts->mutex != NULL)
+		pthread_mutex_lock(ts->mutex);
+	const long it = ts->iteration_being_done - s->batch_first;
+	if (it < 0 || it >= s->batch_count)
+		sts_err(51, __func__, "iteration %ld is not in the current batch", ts->iteration_being_done);
+	const double *pv = s->batch_pvals + it * s->layout.npv + s->layout.pv_off[t];
+	for (int k = 0; k < s->layout.pv_cnt[t]; k++) {
+		const double p_value = pv[k];
+		s->count[t]++;
+		if (p_value == STS_NON_P_VALUE) {
+			/* test not possible for this stream (runs.c:292-323, randomExcursions.c:597-600) */
+		} else {
+			s->valid[t]++;
+			if (p_value < 0.0) {
+				s->failure[t]++;
+				fprintf(stderr, "Warning: iteration %ld of test %s[%d] produced bogus p_value: %f < 0.0\n",
+					ts->iteration_being_done + 1, sts_testNames[t], t, p_value);
+			} else if (p_value > 1.0) {
+				s->failure[t]++;
+				fprintf(stderr, "Warning: iteration %ld of test %s[%d] produced bogus p_value: %f > 1.0\n",
+					ts->iteration_being_done + 1, sts_testNames[t], t, p_value);
+			} else if (p_value < s->tp.alpha) {
+				s->valid_p_val[t]++;
+				s->failure[t]++;
+			} else {
+				s->valid_p_val[t]++;
+				s->success[t]++;
+			}
+		}
+		pv_append(&s->p_val[t], p_value);
+	}
+	if (ts->mutex != NULL)
+		pthread_mutex_unlock(ts->mutex);
+}
+
+#define DEF_ITERATE(NAME, T) static void NAME##_iterate(struct sts_thread_state *ts) { record_test(ts, T); }
+DEF_ITERATE(Frequency, 1) DEF_ITERATE(BlockFrequency, 2) DEF_ITERATE(CumulativeSums, 3) DEF_ITERATE(Runs, 4)
+DEF_ITERATE(LongestRunOfOnes, 5) DEF_ITERATE(Rank, 6) DEF_ITERATE(DiscreteFourierTransform, 7)
+DEF_ITERATE(NonOverlappingTemplateMatchings, 8) DEF_ITERATE(OverlappingTemplateMatchings, 9)
+DEF_ITERATE(Universal, 10) DEF_ITERATE(ApproximateEntropy, 11) DEF_ITERATE(RandomExcursions, 12)
+DEF_ITERATE(RandomExcursionsVariant, 13) DEF_ITERATE(Serial, 14) DEF_ITERATE(LinearComplexity, 15)
+
+static void noop_state(struct sts_state *s) { (void) s; }
+
+/* the plugin table, driver.c:63-192: same order, same five phases */
+const struct sts_driver sts_testDriver[STS_NUMOFTESTS + 1] = {
+	{ NULL, NULL, NULL, NULL, NULL },
+	{ noop_state, Frequency_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, BlockFrequency_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, CumulativeSums_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, Runs_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, LongestRunOfOnes_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, Rank_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, DiscreteFourierTransform_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, NonOverlappingTemplateMatchings_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, OverlappingTemplateMatchings_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, Universal_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, ApproximateEntropy_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, RandomExcursions_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, RandomExcursionsVariant_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, Serial_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, LinearComplexity_iterate, noop_state, noop_state, noop_state },
+};
+
+/* driver.c:395-425 */
+void
+sts_iterate(struct sts_thread_state *ts)
+{
+	if (ts == NULL || ts->global_state == NULL)
+		sts_err(52, __func__, "thread_state arg is NULL");
+	for (int i = 1; i <= STS_NUMOFTESTS; i++)
+		if (ts->global_state->testVector[i] == true)
+			sts_testDriver[i].iterate(ts);
+}
+
+/*
+ * Fill `dst` with `streams` packed streams from the data file.
+ * -F r: the file bytes ARE the packed form (utilities.c:1739-1818 + copyBitsToEpsilon :1837-1884).
+ * -F a: ASCII '0'/'1' characters, whitespace ignored (parseBitsASCIIInput :1651-1727, "%1d"); packed
+ *       MSB first here on the host.
+ * Returns the number of complete streams read (a short raw read is fatal like utilities.c:1789-1791).
+ */
+static long
+read_streams(struct sts_state *s, uint8_t *dst, long streams)
+{
+	const long nb = s->tp.n / 8;
+	if (s->dataFormat == STS_FORMAT_RAW_BINARY) {
+		size_t got = fread(dst, (size_t) nb, (size_t) streams, s->streamFile);
+		if ((long) got != streams)
+			sts_err(213, __func__, "read %zu of %ld streams of %ld bytes from %s: file too short",
+				got, streams, nb, s->randomDataPath);
+		return streams;
+	}
+	for (long k = 0; k < streams; k++) {
+		uint8_t *o = dst + k * nb;
+		memset(o, 0, (size_t) nb);
+		for (long bit = 0; bit < s->tp.n;) {
+			int c = fgetc(s->streamFile);
+			if (c == EOF) {
+				fprintf(stderr, "Warning: insufficient data in %s, %ld bits were read\n", s->randomDataPath,
+					k * s->tp.n + bit);
+				return k;
+			}
+			if (c == '0' || c == '1') {
+				if (c == '1')
+					o[bit >> 3] |= (uint8_t) (0x80u >> (bit & 7));
+				bit++;
+			} else if (c != ' ' && c != '\n' && c != '\r' && c != '\t') {
+				sts_err(214, __func__, "found a character different than 1 or 0 in the sequence: %c", c);
+			}
+		}
+	}
+	return streams;
+}
+
+/*
+ * invokeTestSuite(): replaces the pthread pool of handleFileBasedBitStreams/testBits.  Seek rule of
+ * the reference (utilities.c:1526): job `jobnum` starts at byte jobnum * n * iterations / 8.
+ * Double buffered: while the GPU tests batch k, the host reads batch k+1 into the other pinned buffer.
+ */
+void
+sts_invokeTestSuite(struct sts_state *s)
+{
+	const long nb = s->tp.n / 8;
+	const long B = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
+	s->streamFile = fopen(s->randomDataPath, "rb");
+	if (s->streamFile == NULL)
+		sts_err(210, __func__, "cannot open data file %s: %s", s->randomDataPath, strerror(errno));
+	if (s->jobnum > 0) {
+		const long per_stream = (s->dataFormat == STS_FORMAT_RAW_BINARY) ? nb : s->tp.n;
+		if (fseek(s->streamFile, s->jobnum * per_stream * s->tp.numOfBitStreams, SEEK_SET) != 0)
+			sts_err(211, __func__, "cannot seek to job %ld", s->jobnum);
+	}
+	uint8_t *buf[2];
+	for (int i = 0; i < 2; i++) {
+		buf[i] = stsgpu_host_alloc((size_t) B * (size_t) nb);
+		if (buf[i] == NULL)
+			sts_err(212, __func__, "cannot allocate pinned read buffer of %ld bytes", B * nb);
+	}
+	struct sts_thread_state ts = { 0, s, 0, NULL };
+	long done = 0, cur = 0;
+	long have = read_streams(s, buf[0], B < s->tp.numOfBitStreams ? B : s->tp.numOfBitStreams);
+	while (have > 0) {
+		int rc = stsgpu_submit(s->engine, buf[cur], have, done);
+		if (rc != STSGPU_OK)
+			sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+		long left = s->tp.numOfBitStreams - done - have;
+		long next = 0;
+		if (left > 0)					/* overlap the next read with the GPU */
+			next = read_streams(s, buf[cur ^ 1], left < B ? left : B);
+		rc = stsgpu_wait(s->engine);
+		if (rc != STSGPU_OK)
+			sts_err(216, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+		int64_t bn, bf;
+		stsgpu_results(s->engine, &bn, &bf, &s->batch_pvals, NULL, NULL);
+		s->batch_first = (long) bf;
+		s->batch_count = (long) bn;
+		for (long k = 0; k < have; k++) {		/* iteration order: reproducible .pvalues */
+			ts.iteration_being_done = done + k;
+			sts_iterate(&ts);
+			if (s->reportCycle > 0 && ((done + k + 1) % s->reportCycle) == 0)
+				printf("Completed %ld iterations of %ld\n", done + k + 1, s->tp.numOfBitStreams);
+		}
+		done += have;
+		have = next;
+		cur ^= 1;
+	}
+	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
+	for (int i = 0; i < 2; i++)
+		stsgpu_host_free(buf[i]);
+	fclose(s->streamFile);
+	s->streamFile = NULL;
+}
+
+/* utilities.c:1938-2042: int64 test, int64 count, count doubles, per enabled test; .work then rename */
+void
+sts_write_p_val_to_file(struct sts_state *s)
+{
+	char work[4096], fin[4096];
+	snprintf(work, sizeof(work), "%s/sts.%04ld.%ld.%ld.work", s->workDir, s->jobnum, s->tp.numOfBitStreams, s->tp.n);
+	snprintf(fin, sizeof(fin), "%s/sts.%04ld.%ld.%ld.pvalues", s->workDir, s->jobnum, s->tp.numOfBitStreams, s->tp.n);
+	FILE *f = fopen(work, "wb");
+	if (f == NULL)
+		sts_err(232, __func__, "cannot open %s: %s", work, strerror(errno));
+	for (long i = 1; i <= STS_NUMOFTESTS; i++) {
+		if (s->testVector[i] != true)
+			continue;
+		long cnt = s->p_val[i].count;
+		if (fwrite(&i, sizeof(i), 1, f) != 1 || fwrite(&cnt, sizeof(cnt), 1, f) != 1 ||
+		    (cnt > 0 && fwrite(s->p_val[i].v, sizeof(double), (size_t) cnt, f) != (size_t) cnt))
+			sts_err(232, __func__, "error while writing p-values of test %ld to %s", i, work);
+	}
+	fclose(f);
+	if (rename(work, fin) < 0)
+		sts_err(232, __func__, "error in renaming %s to %s", work, fin);
+}
+
+void
+sts_destroy(struct sts_state *s)
+{
+	if (s->engine)
+		stsgpu_destroy(s->engine);
+	s->engine = NULL;
+	for (int t = 0; t <= STS_NUMOFTESTS; t++) {
+		free(s->p_val[t].v);
+		s->p_val[t].v = NULL;
+	}
+	free(s->workDir);
+	free(s->randomDataPath);
+	s->workDir = s->randomDataPath = NULL;
+}

@@ -1,0 +1,106 @@
+/*
+ * stsb200.c - the reference's main() sequence (src/sts.c:317-399) for the hot path:
+ *     parse_args -> init -> invokeTestSuite -> write_p_val_to_file -> destroy
+ * with the reference's flag letters and meanings for everything the path needs
+ * (-i -S -P -T -j -m -F -t -w -v -I; parse_args.c:426-957).  Assessment (result.txt) is not rebuilt:
+ * run the reference itself on the .pvalues this program writes:  sts -m a -d <workDir> ...
+ */
+#define _GNU_SOURCE
+#include <getopt.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sts_host.h"
+
+static const char *usage =
+	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
+	"               [-I reportCycle] [-w workDir] [-F r|a] [-j jobnum] [-m b|i] [-T threads] [-B batch] [-D device] datafile\n"
+	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
+	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues;\n"
+	"  assess with the reference: sts -m a -d workDir -i <total iterations> ...\n";
+
+int
+main(int argc, char **argv)
+{
+	struct sts_state st;
+	sts_defaultstate(&st);
+	int opt;
+	char *brkt, *phrase;
+	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:h")) != -1) {
+		switch (opt) {
+		case 'v': st.debuglevel = atoi(optarg); break;
+		case 't':
+			st.testVectorFlag = true;
+			for (phrase = strtok_r(optarg, ",", &brkt); phrase; phrase = strtok_r(NULL, ",", &brkt)) {
+				long t = atol(phrase);
+				if (t == 0)
+					for (int i = 1; i <= STS_NUMOFTESTS; i++) st.testVector[i] = true;
+				else if (t < 0 || t > STS_NUMOFTESTS)
+					sts_err(1, __func__, "-t test: %ld must be in the range [0-%d]", t, STS_NUMOFTESTS);
+				else
+					st.testVector[t] = true;
+			}
+			break;
+		case 'P':
+			for (phrase = strtok_r(optarg, ",", &brkt); phrase; phrase = strtok_r(NULL, ",", &brkt)) {
+				long num, value;
+				double d;
+				if (sscanf(phrase, "%ld=", &num) != 1 || num < 1 || num > 11)
+					sts_err(1, __func__, "-P num=value[,num=value].. num must be in the range [1-11]: %s", phrase);
+				if (num <= 9) {
+					if (sscanf(phrase, "%ld=%ld", &num, &value) != 2)
+						sts_err(1, __func__, "-P expected integer=integer: %s", phrase);
+					sts_change_params(&st, num, value, 0.0);
+				} else {
+					if (sscanf(phrase, "%ld=%lf", &num, &d) != 2)
+						sts_err(1, __func__, "-P expected integer=float: %s", phrase);
+					sts_change_params(&st, num, 0, d);
+				}
+			}
+			break;
+		case 'S': st.tp.n = atol(optarg); break;
+		case 'i': st.tp.numOfBitStreams = atol(optarg); break;
+		case 'I': st.reportCycle = atol(optarg); break;
+		case 'w': free(st.workDir); st.workDir = strdup(optarg); break;
+		case 'F':
+			if (optarg[0] != 'r' && optarg[0] != 'a')
+				sts_err(1, __func__, "-F format: %s must be r or a", optarg);
+			st.dataFormat = (enum sts_format) optarg[0];
+			break;
+		case 'j': st.jobnum = atol(optarg); break;
+		case 'm':
+			if (optarg[0] == 'b') st.runMode = STS_MODE_ITERATE_AND_ASSESS;
+			else if (optarg[0] == 'i') st.runMode = STS_MODE_ITERATE_ONLY;
+			else sts_err(1, __func__, "-m %s: only b and i run on the GPU; use the reference's sts -m a to assess", optarg);
+			break;
+		case 'T': st.numberOfThreads = atol(optarg); break;
+		case 'B': st.batchStreams = atol(optarg); break;
+		case 'D': st.device = atoi(optarg); break;
+		case 'h':
+		default:
+			fputs(usage, stderr);
+			return opt == 'h' ? 0 : 1;
+		}
+	}
+	if (optind != argc - 1) {
+		fputs(usage, stderr);
+		return 1;
+	}
+	st.randomDataPath = strdup(argv[optind]);
+	if (!st.testVectorFlag)				/* parse_args.c: no -t means all tests */
+		for (int i = 1; i <= STS_NUMOFTESTS; i++) st.testVector[i] = true;
+	if (st.tp.numOfBitStreams < 1)
+		sts_err(1, __func__, "-i iterations: %ld must be > 0", st.tp.numOfBitStreams);
+
+	sts_init(&st);
+	sts_invokeTestSuite(&st);
+	sts_write_p_val_to_file(&st);
+	if (st.debuglevel > 0) {
+		for (int t = 1; t <= STS_NUMOFTESTS; t++)
+			if (st.testVector[t])
+				printf("%-26s count %8ld valid %8ld success %8ld failure %8ld\n", sts_testNames[t], st.count[t],
+				       st.valid[t], st.success[t], st.failure[t]);
+		printf("wrote %s/sts.%04ld.%ld.%ld.pvalues\n", st.workDir, st.jobnum, st.tp.numOfBitStreams, st.tp.n);
+	}
+	sts_destroy(&st);
+	return 0;
+}

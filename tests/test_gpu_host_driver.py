@@ -1,0 +1,102 @@
+"""GPU (-m gpu): the C host driver (sts_b200/host/stsb200, the reference's main() sequence for the
+hot path) end to end: same flags, same .pvalues bytes layout, and - when the prebuilt reference binary
+travelled with the repo (oracle/_ref/sts) - the SAME result.txt as the reference run on the same file
+(north star: "matching result.txt")."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STSB200 = os.path.join(ROOT, "sts_b200", "host", "stsb200")
+REF = os.path.join(ROOT, "oracle", "_ref", "sts")
+
+
+def read_pvalues(path):
+    buf = open(path, "rb").read()
+    off, out = 0, {}
+    while off < len(buf):
+        t, cnt = struct.unpack_from("<qq", buf, off)
+        off += 16
+        out[t] = np.frombuffer(buf, dtype="<f8", count=cnt, offset=off).copy()
+        off += 8 * cnt
+    return out
+
+
+def result_body(path):
+    txt = open(path).read()
+    return txt[txt.index("- - - -"):]        # the header names the data source, the rest must be identical
+
+
+@pytest.fixture(scope="module")
+def lcg8(tmp_path_factory, oracle):
+    d = tmp_path_factory.mktemp("lcg")
+    p = str(d / "lcg8.bin")
+    oracle.lcg_bytes(0, 8).tofile(p)
+    return p
+
+
+def run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, "%s\n%s" % (" ".join(cmd), r.stdout[-2000:])
+    return r.stdout
+
+
+def test_pvalues_file_matches_reference_golden(lcg8, tmp_path):
+    assert os.path.exists(STSB200), "host driver not built (make -C sts_b200)"
+    w = str(tmp_path / "w")
+    run([STSB200, "-m", "i", "-i", "8", "-F", "r", "-B", "3", "-w", w, lcg8])      # -B 3: ragged batches 3+3+2
+    pv = read_pvalues(os.path.join(w, "sts.0000.8.1048576.pvalues"))
+    g = load_golden("lcg_default_8")
+    assert sorted(pv) == list(range(1, 16))
+    for t in range(1, 16):
+        ref = g["pv_%d" % t]
+        mine = pv[t].reshape(ref.shape)          # iteration-major, like the reference with -T 1
+        assert rel_err(mine, ref).max() <= 1e-9, "test %d" % t
+
+
+def test_result_txt_identical_to_reference(lcg8, tmp_path):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    w = str(tmp_path / "gpu")
+    run([STSB200, "-m", "i", "-i", "8", "-F", "r", "-w", w, lcg8])
+    run([REF, "-v", "0", "-m", "a", "-d", w, "-i", "8", "-w", str(tmp_path / "assess")])
+    run([REF, "-v", "0", "-i", "8", "-T", "8", "-F", "r", "-w", str(tmp_path / "ref"), lcg8])
+    a = result_body(str(tmp_path / "assess" / "result.txt"))
+    b = result_body(str(tmp_path / "ref" / "result.txt"))
+    assert a == b
+
+
+def test_jobnum_and_ascii_input(lcg8, tmp_path, oracle):
+    w = str(tmp_path / "j")
+    run([STSB200, "-m", "i", "-i", "4", "-j", "1", "-t", "1,3,8,15", "-w", w, lcg8])   # second half of the file
+    pv = read_pvalues(os.path.join(w, "sts.0001.4.1048576.pvalues"))
+    g = load_golden("lcg_default_8")
+    assert sorted(pv) == [1, 3, 8, 15]
+    for t in (1, 3, 8, 15):
+        ref = g["pv_%d" % t][4:]
+        assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9
+    # -F a: the same first stream as ASCII 0/1 characters with line breaks
+    bits = np.unpackbits(oracle.lcg_bytes(0, 1))
+    txt = "\n".join("".join("01"[b] for b in bits[i:i + 64]) for i in range(0, bits.size, 64))
+    ap = str(tmp_path / "ascii.txt")
+    open(ap, "w").write(txt + "\n")
+    wa = str(tmp_path / "a")
+    run([STSB200, "-m", "i", "-i", "1", "-F", "a", "-w", wa, ap])
+    pa = read_pvalues(os.path.join(wa, "sts.0000.1.1048576.pvalues"))
+    for t in range(1, 16):
+        ref = g["pv_%d" % t][:1]
+        assert rel_err(pa[t].reshape(ref.shape), ref).max() <= 1e-9
+
+
+def test_short_file_is_fatal(tmp_path):
+    p = str(tmp_path / "short.bin")
+    open(p, "wb").write(b"\x00" * 1000)
+    r = subprocess.run([STSB200, "-i", "1", "-w", str(tmp_path / "s"), p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 213                   # utilities.c:1789-1791: a short raw read is fatal
