@@ -2,7 +2,8 @@
  * k_dft_fast.cu - the DFT test's four-step FFT specialised for n = 2^20 (N = 2^19 = 512 x 1024), the
  * stream length of the headline benchmark.  Same algorithm and same tables as k_dft.cu (which stays
  * as the generic power-of-two path); here every size is a compile-time constant so the index
- * arithmetic folds away, each CTA is 256 threads with <= 85 registers (3 CTAs per SM), and the
+ * arithmetic folds away, every table is laid out so that a warp's lookups are contiguous (the LSU
+ * wavefront count, not FP64, bounded the first version), each CTA is 256 threads with <= 85 registers (3 CTAs per SM), and the
  * real-FFT post pass handles bins q and N - q together:
  *     A = (Z_q + conj Z_{N-q}) / 2,  B = -(i/2) W_n^q (Z_q - conj Z_{N-q})
  *     X_q = A + B,   X_{N-q} = conj(A - B)
@@ -49,7 +50,7 @@ dft_cols_fast(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *
 		const int k = t & 7;
 #pragma unroll
 		for (int r = 1; r < 8; r++)
-			v[r] = cmul(v[r], __ldg(D.wm + 16 * k * r));
+			v[r] = cmul(v[r], __ldg(D.tw8 + (r - 1) * 8 + k));
 		bfly<8>(v);
 		__syncthreads();
 		const int base = (t - k) * 8 + k;
@@ -65,14 +66,11 @@ dft_cols_fast(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *
 		v[r] = buf[padi(t + 64 * r) * FCW + c];
 #pragma unroll
 	for (int r = 1; r < 8; r++)
-		v[r] = cmul(v[r], __ldg(D.wm + 2 * t * r));
+		v[r] = cmul(v[r], __ldg(D.tw64 + (r - 1) * 64 + t));
 	bfly<8>(v);
 #pragma unroll
 	for (int r = 0; r < 8; r++) {
-		const int k1 = t + 64 * r;
-		const int e = j2 * k1;
-		const double2 tw = cmul(__ldg(D.th + (e >> 10)), __ldg(D.tl + (e & 1023)));
-		Ys[k1 * FN2 + j2] = cmul(v[r], tw);
+		Ys[(t + 64 * r) * FN2 + j2] = v[r];	/* the W_N^(j2 k1) factor is applied by the row pass */
 	}
 }
 
@@ -88,6 +86,7 @@ dft_rows_fast(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *
 	const int rho = threadIdx.x >> 7, t = threadIdx.x & 127;
 	const bool active = (rho == 0) || !self;
 	const double2 *__restrict__ src = Ys + (rho ? k1b : k1a) * FN2;
+	const double2 *__restrict__ twr = D.tw2d + (rho ? k1b : k1a) * FN2;
 	double2 *row = buf + rho * ROWLEN;
 	if (threadIdx.x == 0)
 		cnt_s = 0;
@@ -97,7 +96,7 @@ dft_rows_fast(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *
 	if (active) {
 #pragma unroll
 		for (int r = 0; r < 8; r++)
-			v[r] = src[t + 128 * r];
+			v[r] = cmul(src[t + 128 * r], __ldg(twr + t + 128 * r));	/* times W_N^(j2 k1) */
 		bfly<8>(v);
 #pragma unroll
 		for (int r = 0; r < 8; r++)
@@ -113,10 +112,10 @@ dft_rows_fast(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *
 #pragma unroll
 			for (int r = 0; r < 8; r++)
 				v[r] = row[padi(t + 128 * r)];
-			const int step = 1024 / (Ns * 8);
+			const double2 *__restrict__ tw = (pass == 1) ? D.tw8 : D.tw64;
 #pragma unroll
 			for (int r = 1; r < 8; r++)
-				v[r] = cmul(v[r], __ldg(D.wm + k * r * step));
+				v[r] = cmul(v[r], __ldg(tw + (r - 1) * Ns + k));
 			bfly<8>(v);
 		}
 		__syncthreads();

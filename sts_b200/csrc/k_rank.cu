@@ -1,92 +1,112 @@
 /*
  * k_rank.cu - binary matrix rank test (rank.c:303-327 with utils/matrix.c:49-200).
  *
- * One 32x32 matrix per warp, one row per lane as a packed 32-bit word (row i of matrix k is
- * stream word 32k + i, def_matrix matrix.c:284-288; column j is bit 31 - j).  The statistic is NOT
- * the mathematical GF(2) rank: it is the number of non-zero rows left by NIST's schedule - forward
- * elimination for i = 0..30 (pivot search downwards, first hit), then backward elimination for
- * i = 31..1 (pivot search upwards, first hit) - which this kernel follows step by step with
- * ballot (pivot search) and shuffles (row swap / pivot broadcast).  Whole-row XOR equals the
- * reference's partial-row XOR because columns < i of rows >= i are already zero in the forward pass.
+ * One 32x32 matrix per THREAD: the 32 rows live in 32 registers as packed words (row i of matrix k
+ * is stream word 32k + i, def_matrix matrix.c:284-288; column j is bit 31 - j) and the whole
+ * elimination is straight-line, branch-free register code - no shuffles, no ballots, no divergence.
+ * The statistic is NOT the mathematical GF(2) rank: it is the number of non-zero rows left by
+ * NIST's schedule - forward elimination for i = 0..30 (pivot search downwards, first hit), then
+ * backward elimination for i = 31..1 (pivot search upwards, first hit).  Search, swap and
+ * elimination of one column are fused into one sweep over the rows r beyond i with the pivot
+ * candidate p carried in a register:
+ *     row r has the bit, p has not  ->  swap (p, row r)          (matrix.c:90-133 first hit + swap)
+ *     row r has the bit, p has it   ->  row r ^= p                (matrix.c:64-67 / :79-82)
+ * which visits the rows in the reference's order, so the first row with the bit becomes the pivot
+ * and every later one is reduced by it; a column without any pivot leaves all rows untouched.
+ * Whole-row XOR equals the reference's partial-row XOR because the columns already processed are
+ * zero in the rows still being combined.
  *
- * Algorithmic bytes: n/8 per stream (each word is read exactly once, 128-byte coalesced).
+ * A CTA stages its 128 matrices (16 KiB of the stream, 128-bit coalesced loads) in shared memory
+ * with a 33-word pitch so that the per-thread row reads are bank-conflict free.
+ *
+ * Algorithmic bytes: n/8 per stream (each word is read exactly once).
  */
 #include "common.cuh"
 
-#define RANK_WARPS 8
+#define RANK_THREADS 128
 
-__device__ __forceinline__ int nist_rank32(uint32_t row, int lane)
+__device__ __forceinline__ int nist_rank32_regs(uint32_t (&row)[32])
 {
 	/* forward, matrix.c:59-69 */
+#pragma unroll
 	for (int i = 0; i < 31; i++) {
-		const int sh = 31 - i;
-		uint32_t colbit = (row >> sh) & 1u;
-		uint32_t col = __ballot_sync(0xffffffffu, colbit);
-		if (!((col >> i) & 1u)) {
-			uint32_t cand = col & (0xFFFFFFFEu << i);	/* rows > i */
-			if (cand == 0)
-				continue;
-			int idx = __ffs(cand) - 1;			/* first row below */
-			uint32_t ri = __shfl_sync(0xffffffffu, row, i);
-			uint32_t rx = __shfl_sync(0xffffffffu, row, idx);
-			if (lane == i)
-				row = rx;
-			else if (lane == idx)
-				row = ri;
-			colbit = (row >> sh) & 1u;
+		const uint32_t bit = 0x80000000u >> i;
+		uint32_t p = row[i];
+		bool ph = (p & bit) != 0u;
+#pragma unroll
+		for (int r = i + 1; r < 32; r++) {
+			const uint32_t x = row[r];
+			const bool t = (x & bit) != 0u;
+			const uint32_t xp = x ^ p;
+			row[r] = t ? (ph ? xp : p) : x;
+			p = (t && !ph) ? x : p;
+			ph = ph || t;
 		}
-		uint32_t prow = __shfl_sync(0xffffffffu, row, i);
-		if (lane > i && colbit)
-			row ^= prow;
+		row[i] = p;
 	}
 	/* backward, matrix.c:74-84 */
+#pragma unroll
 	for (int i = 31; i > 0; i--) {
-		const int sh = 31 - i;
-		uint32_t colbit = (row >> sh) & 1u;
-		uint32_t col = __ballot_sync(0xffffffffu, colbit);
-		if (!((col >> i) & 1u)) {
-			uint32_t cand = col & ((1u << i) - 1u);		/* rows < i */
-			if (cand == 0)
-				continue;
-			int idx = 31 - __clz(cand);			/* first row above */
-			uint32_t ri = __shfl_sync(0xffffffffu, row, i);
-			uint32_t rx = __shfl_sync(0xffffffffu, row, idx);
-			if (lane == i)
-				row = rx;
-			else if (lane == idx)
-				row = ri;
-			colbit = (row >> sh) & 1u;
+		const uint32_t bit = 0x80000000u >> i;
+		uint32_t p = row[i];
+		bool ph = (p & bit) != 0u;
+#pragma unroll
+		for (int r = i - 1; r >= 0; r--) {
+			const uint32_t x = row[r];
+			const bool t = (x & bit) != 0u;
+			const uint32_t xp = x ^ p;
+			row[r] = t ? (ph ? xp : p) : x;
+			p = (t && !ph) ? x : p;
+			ph = ph || t;
 		}
-		uint32_t prow = __shfl_sync(0xffffffffu, row, i);
-		if (lane < i && colbit)
-			row ^= prow;
+		row[i] = p;
 	}
-	return __popc(__ballot_sync(0xffffffffu, row != 0u));	/* matrix.c:162-188 */
+	int rank = 0;							/* matrix.c:162-188 */
+#pragma unroll
+	for (int i = 0; i < 32; i++)
+		rank += (row[i] != 0u) ? 1 : 0;
+	return rank;
 }
 
-__global__ void __launch_bounds__(RANK_WARPS * 32)
+__global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st)
 {
+	__shared__ uint32_t tile[RANK_THREADS * 33];
 	__shared__ unsigned int f[2];
 	const int64_t s = blockIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x < 2)
-		f[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t *__restrict__ w = in + s * P.pitch_words;
-	unsigned int f32 = 0, f31 = 0;
-	for (int64_t k = (int64_t) blockIdx.y * RANK_WARPS + warp; k < P.rank_count; k += (int64_t) gridDim.y * RANK_WARPS) {
-		uint32_t row = ldw(w, k * 32 + lane);
-		int R = nist_rank32(row, lane);
-		f32 += (R == 32);
-		f31 += (R == 31);
+	const int tid = threadIdx.x;
+	if (tid < 2)
+		f[tid] = 0;
+	const int64_t m0 = (int64_t) blockIdx.y * RANK_THREADS;		/* first matrix of this CTA */
+	const int nm = (int) min((int64_t) RANK_THREADS, P.rank_count - m0);
+	const uint4 *__restrict__ src = (const uint4 *) (in + s * P.pitch_words + m0 * 32);
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int q = tid + RANK_THREADS * j;			/* 16-byte unit inside the tile */
+		const int m = q >> 3, c = (q & 7) * 4;
+		if (m < nm) {
+			const uint4 v = __ldg(src + q);
+			uint32_t *d = tile + m * 33 + c;
+			d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+		}
 	}
-	if (lane == 0) {
-		if (f32) atomicAdd(&f[0], f32);
-		if (f31) atomicAdd(&f[1], f31);
+	__syncthreads();
+	int R = -1;
+	if (tid < nm) {
+		uint32_t row[32];
+#pragma unroll
+		for (int i = 0; i < 32; i++)
+			row[i] = bswap32(tile[tid * 33 + i]);
+		R = nist_rank32_regs(row);
+	}
+	const unsigned int b32 = __popc(__ballot_sync(0xffffffffu, R == 32));
+	const unsigned int b31 = __popc(__ballot_sync(0xffffffffu, R == 31));
+	if ((tid & 31) == 0) {
+		if (b32) atomicAdd(&f[0], b32);
+		if (b31) atomicAdd(&f[1], b31);
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
+	if (tid == 0) {
 		unsigned long long *o = (unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_RANK]);
 		if (f[0]) atomicAdd(&o[0], (unsigned long long) f[0]);
 		if (f[1]) atomicAdd(&o[1], (unsigned long long) f[1]);
@@ -96,12 +116,9 @@ rank_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 
 cudaError_t launch_rank(const DevParams &P, const LaunchCtx &L)
 {
-	if (!(P.enabled & (1u << STSGPU_TEST_RANK)))
+	if (!(P.enabled & (1u << STSGPU_TEST_RANK)) || P.rank_count < 1)
 		return cudaSuccess;
-	int64_t gy = (P.rank_count + RANK_WARPS * 16 - 1) / (RANK_WARPS * 16);	/* >= 16 matrices per warp */
-	if (gy < 1) gy = 1;
-	if (gy > 64) gy = 64;
-	dim3 grid((unsigned) L.nstreams, (unsigned) gy);
-	rank_kernel<<<grid, RANK_WARPS * 32, 0, L.stream>>>(P, L.d_in, L.d_st);
+	dim3 grid((unsigned) L.nstreams, (unsigned) ((P.rank_count + RANK_THREADS - 1) / RANK_THREADS));
+	rank_kernel<<<grid, RANK_THREADS, 0, L.stream>>>(P, L.d_in, L.d_st);
 	return cudaGetLastError();
 }

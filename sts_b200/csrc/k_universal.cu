@@ -4,51 +4,201 @@
  * The statistic is  sum += log(i - T[block_i]) / log(2)  over K = 1000 * 2^L test blocks, a
  * sequential double-precision sum of 128000 terms at L = 7 whose rounding depends on the order.
  * To reproduce the reference's value bit for bit the kernel
- *   - finds every distance i - T[.] exactly (integers): a warp takes 32 consecutive L-bit blocks,
- *     `match.any` resolves repeats inside the warp and a shared-memory table T[2^L] carries the
- *     last occurrence across rows (table starts at 0 like the reference's memset, universal.c:327);
+ *   - finds every distance i - T[.] exactly (integers): a warp takes 32 consecutive L-bit blocks
+ *     (one "row"), `match.any` resolves repeats inside the row and a shared-memory table T[2^L]
+ *     carries the last occurrence across rows (table starts at 0 like the reference's memset,
+ *     universal.c:327);
  *   - looks the term up in a table log2tab[d] = log(d) / log(2.0) computed ON THE HOST with the
  *     reference's expression and libm, so each addend is the reference's double;
- *   - adds the 32 terms of a row in block order, one after the other (shuffle + DADD chain).
- * One warp per stream; the DADD dependency chain is the cost (~10 cycles per block), which other
- * kernels on other streams hide.
+ *   - reproduces the sequential round-to-nearest-even accumulation EXACTLY but in parallel: while
+ *     the running sum s stays inside one binade [2^k, 2^(k+1)) it is an integer S in units of
+ *     u = 2^(k-52), and adding a term x >= 0 is  S -> S + round(x / u)  where only a tie
+ *     (x / u = q + 1/2) depends on the state, through the parity of S.  Every term is therefore a
+ *     map  S -> S + (S even ? a0 : a1)  with |a1 - a0| <= 1; these maps are closed under
+ *     composition, so 128 terms (4 rows) are composed 4 per lane and then by a 5-step warp
+ *     butterfly.  A group that would leave the binade (about 14 of 1010 groups at L = 7), or that
+ *     starts below 2^6, is added term by term with DADD in block order instead.
  *
- * Algorithmic bytes: ceil((Q + K) * L / 8) per stream (113120 at L = 7) + the L2-resident table.
+ * One warp per stream (one CTA = one warp).  The packed stream is staged through shared memory in
+ * "super rows" of 32 L words = 1024 blocks with cp.async, double buffered, so DRAM latency is off
+ * the dependency chain; what remains is the T[] chain (LDS -> STS per row).
+ *
+ * Algorithmic bytes: ceil((Q + K) * L / 8) per stream (113120 at L = 7) + the L1/L2-resident table.
  */
 #include "common.cuh"
+
+#define UNI_GROUP 4			/* rows per summation group */
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc)
+{
+	const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+/* one addend as a map S -> S + (S even ? a0 : a0 + dl) in units of 2^(k-52); needs k >= 6 > exponent(x) + 1 */
+struct RneMap {
+	unsigned long long a0;
+	int dl;
+};
+
+__device__ __forceinline__ RneMap rne_of_term(double x, int k)
+{
+	RneMap f;
+	f.a0 = 0;
+	f.dl = 0;
+	const unsigned long long xb = (unsigned long long) __double_as_longlong(x);
+	if (xb != 0) {
+		const int e = (int) (xb >> 52) - 1023;
+		const unsigned long long M = (xb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+		int sh = k - e;
+		sh = sh > 62 ? 62 : sh;
+		unsigned long long q = M >> sh;
+		const unsigned long long r = M & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+		if (r > half) {
+			q++;
+		} else if (r == half) {			/* tie: the result must be even */
+			f.dl = (q & 1ull) ? -1 : 1;
+			q += (q & 1ull);
+		}
+		f.a0 = q;
+	}
+	return f;
+}
+
+/* f first, then g */
+__device__ __forceinline__ RneMap rne_compose(const RneMap &f, const RneMap &g)
+{
+	const unsigned long long f1 = f.a0 + (long long) f.dl;
+	const unsigned long long g1 = g.a0 + (long long) g.dl;
+	const unsigned long long h0 = f.a0 + ((f.a0 & 1ull) ? g1 : g.a0);
+	const unsigned long long h1 = f1 + ((f1 & 1ull) ? g.a0 : g1);
+	RneMap h;
+	h.a0 = h0;
+	h.dl = (int) (long long) (h1 - h0);
+	return h;
+}
 
 __global__ void __launch_bounds__(32)
 universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__restrict__ log2tab,
 		 long long *__restrict__ st)
 {
-	extern __shared__ uint32_t T[];
+	extern __shared__ __align__(16) uint32_t usm[];
+	const int L = P.univ_L;
+	const int IB = 32 * L + 2;				/* one super row + pad word, even */
+	double *tbuf = (double *) usm;				/* [UNI_GROUP * 32] terms in block order */
+	uint32_t *ibuf = usm + 2 * UNI_GROUP * 32;		/* [2][IB] staged input */
+	uint32_t *T = ibuf + 2 * IB;				/* [2^L] */
 	const int64_t s = blockIdx.x;
 	const int lane = threadIdx.x;
-	const int L = P.univ_L;
 	const uint32_t *__restrict__ w = in + s * P.pitch_words;
 	for (int i = lane; i < (1 << L); i += 32)
 		T[i] = 0;
-	__syncwarp();
+	if (lane < 2)
+		ibuf[lane * IB + 32 * L] = 0;			/* pad words (read, never used) */
 	const int64_t Q = P.univ_Q, K = P.univ_K;
+	const int rows = (int) ((Q + K) >> 5);			/* 1010 * 2^(L-5), a multiple of UNI_GROUP for L >= 6 */
+	const int qrows = (int) (Q >> 5);
+	const int nsr = (rows + 31) >> 5;
+
+	auto stage = [&](int sr) {
+		uint32_t *dst = ibuf + (sr & 1) * IB;
+		const int64_t g0 = (int64_t) sr * 32 * L + lane;
+		for (int j = 0; j < L; j++) {
+			const int64_t g = g0 + 32 * j;
+			if (g < P.pitch_words)
+				cp_async4(dst + 32 * j + lane, w + g);
+		}
+		cp_async_commit();
+	};
+
 	double sum = 0.0;
-	for (int64_t base = 0; base < Q + K; base += 32) {
-		const int64_t i = base + lane + 1;			/* 1-based block number */
-		const uint32_t v = get32(w, (i - 1) * L) >> (32 - L);
-		const uint32_t same = __match_any_sync(0xffffffffu, v);
-		const uint32_t lower = same & ((1u << lane) - 1u);
-		const bool is_last = (same >> lane) <= 1u;		/* no higher lane holds the same pattern */
-		if (base >= Q) {
-			uint32_t prev = lower ? (uint32_t) (base + (31 - __clz(lower)) + 1) : T[v];
-			double term = __ldg(log2tab + (i - prev));
-			/* universal.c:369: sequential accumulation in block order */
-#pragma unroll
-			for (int l = 0; l < 32; l++)
-				sum += __shfl_sync(0xffffffffu, term, l);
+	stage(0);
+	for (int sr = 0; sr < nsr; sr++) {
+		if (sr + 1 < nsr) {
+			stage(sr + 1);
+			cp_async_wait<1>();
+		} else {
+			cp_async_wait<0>();
 		}
 		__syncwarp();
-		if (is_last)
-			T[v] = (uint32_t) i;
-		__syncwarp();
+		const uint32_t *buf = ibuf + (sr & 1) * IB;
+		const int row_end = min(32, rows - sr * 32);
+		for (int rg = 0; rg < row_end; rg += UNI_GROUP) {
+			const int row0 = sr * 32 + rg;
+			const bool testing = row0 >= qrows;
+			/* phase A: the four rows' patterns and their in-row repeats (independent of T[]) */
+			uint32_t v[UNI_GROUP], lower[UNI_GROUP], tprev[UNI_GROUP];
+			bool is_last[UNI_GROUP];
+#pragma unroll
+			for (int r4 = 0; r4 < UNI_GROUP; r4++) {
+				const int off = ((rg + r4) * 32 + lane) * L;	/* bit offset inside the super row */
+				const uint32_t hi = bswap32(buf[off >> 5]), lo = bswap32(buf[(off >> 5) + 1]);
+				v[r4] = __funnelshift_l(lo, hi, off & 31) >> (32 - L);
+				const uint32_t same = __match_any_sync(0xffffffffu, v[r4]);
+				lower[r4] = same & ((1u << lane) - 1u);
+				is_last[r4] = (same >> lane) <= 1u;	/* no higher lane holds the same pattern */
+			}
+			/* phase B: the T[] chain; the loaded values are only consumed in phase C */
+#pragma unroll
+			for (int r4 = 0; r4 < UNI_GROUP; r4++) {
+				tprev[r4] = T[v[r4]];
+				__syncwarp();
+				if (is_last[r4])
+					T[v[r4]] = (uint32_t) (row0 + r4) * 32u + lane + 1u;	/* 1-based block number */
+				__syncwarp();
+			}
+			/* phase C: distances -> terms, in block order in tbuf */
+			if (testing) {
+				double term[UNI_GROUP];
+#pragma unroll
+				for (int r4 = 0; r4 < UNI_GROUP; r4++) {
+					const uint32_t i = (uint32_t) (row0 + r4) * 32u + lane + 1u;
+					const uint32_t prev = lower[r4] ? (i - lane + (31 - __clz(lower[r4]))) : tprev[r4];
+					term[r4] = __ldg(log2tab + (i - prev));
+				}
+#pragma unroll
+				for (int r4 = 0; r4 < UNI_GROUP; r4++)
+					tbuf[r4 * 32 + lane] = term[r4];
+				__syncwarp();
+			}
+			if (!testing)
+				continue;
+			/* universal.c:369: sequential accumulation in block order, reproduced exactly */
+			const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
+			const int k = (int) (sb >> 52) - 1023;
+			bool fast = k >= 6;
+			unsigned long long Snew = 0;
+			if (fast) {
+				const double4 ta = *(const double4 *) (tbuf + 4 * lane);
+				RneMap f = rne_of_term(ta.x, k);
+				f = rne_compose(f, rne_of_term(ta.y, k));
+				f = rne_compose(f, rne_of_term(ta.z, k));
+				f = rne_compose(f, rne_of_term(ta.w, k));
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					RneMap g;
+					const uint32_t plo = __shfl_xor_sync(0xffffffffu, (uint32_t) f.a0, o);
+					const uint32_t phi = __shfl_xor_sync(0xffffffffu, (uint32_t) (f.a0 >> 32) | ((uint32_t) (f.dl + 1) << 30), o);
+					g.a0 = ((unsigned long long) (phi & 0x3FFFFFFFu) << 32) | plo;
+					g.dl = (int) (phi >> 30) - 1;
+					f = (lane & o) ? rne_compose(g, f) : rne_compose(f, g);
+				}
+				const unsigned long long S = (sb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+				Snew = S + ((S & 1ull) ? f.a0 + (long long) f.dl : f.a0);
+				fast = Snew < 0x0020000000000000ull;	/* still inside the binade */
+			}
+			if (fast) {
+				sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) |
+									(Snew & 0x000FFFFFFFFFFFFFull)));
+			} else {
+#pragma unroll 8
+				for (int j = 0; j < UNI_GROUP * 32; j++)
+					sum += tbuf[j];
+			}
+			__syncwarp();				/* tbuf is rewritten by the next group */
+		}
 	}
 	if (lane == 0)
 		st[s * P.nst + P.st_off[STSGPU_TEST_UNIVERSAL]] = __double_as_longlong(sum);
@@ -58,8 +208,8 @@ cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const doubl
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_UNIVERSAL)))
 		return cudaSuccess;
-	size_t smem = (size_t) sizeof(uint32_t) << P.univ_L;
-	cudaError_t e = cudaFuncSetAttribute(universal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	const size_t smem = sizeof(uint32_t) * ((size_t) 2 * UNI_GROUP * 32 + 2 * (32 * P.univ_L + 2) + ((size_t) 1 << P.univ_L));
+	cudaError_t e = cudaFuncSetAttribute(universal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
 	if (e != cudaSuccess)
 		return e;
 	universal_kernel<<<(unsigned) L.nstreams, 32, smem, L.stream>>>(P, L.d_in, d_log2_table, L.d_st);
