@@ -78,6 +78,111 @@ lc_kernel_reg(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__res
 			  (unsigned long long) cls[threadIdx.x]);
 }
 
+/*
+ * Windowed variant (M <= 511): at step N only the words between the lowest and the highest non-zero
+ * coefficient carry information.  C (= c reversed, aligned at N) is non-zero on positions [N - L, N]
+ * and B (= C at the last length change, fixed in place) on positions [L - 1 ..]; for every step N'
+ * of a 32-step phase starting at N0 both lie above  min(N0 - L_N0, L_N0 - 1)  because L never shrinks
+ * and a length change at N sets L to N + 1 - L_old <= N' - L_N0.  The phase index fixes the top word
+ * at compile time, the bottom word is the warp-wide minimum of that bound, and the pair selects one
+ * of ~150 straight-line step bodies, so the registers stay statically indexed.  For random input
+ * L tracks N/2 and the window is about N/64 + 2 words instead of 16.
+ */
+template <int W, int LO, int HI>
+__device__ __forceinline__ void lc_steps(const uint32_t (&S)[W], uint32_t (&C)[W], uint32_t (&B)[W], int &L, int N0, int N1)
+{
+	for (int N = N0; N < N1; N++) {
+		uint32_t acc = 0;
+#pragma unroll
+		for (int i = LO; i <= HI; i++)
+			acc ^= C[i] & S[i];
+		const uint32_t d = (uint32_t) __popc(acc) & 1u;
+		const uint32_t dm = 0u - d;
+		const uint32_t um = (2 * L <= N) ? dm : 0u;
+		uint32_t prev = 0;
+#pragma unroll
+		for (int i = LO; i <= HI; i++) {
+			const uint32_t c_old = C[i];
+			const uint32_t c_new = c_old ^ (B[i] & dm);
+			B[i] = (c_old & um) | (B[i] & ~um);
+			C[i] = (c_new >> 1) | (prev << 31);	/* advance to N + 1 */
+			prev = c_new;
+		}
+		L = um ? (N + 1 - L) : L;
+	}
+}
+
+template <int W, int LO, int HI>
+__device__ __forceinline__ void lc_dispatch(int lo, const uint32_t (&S)[W], uint32_t (&C)[W], uint32_t (&B)[W], int &L, int N0,
+					    int N1)
+{
+	if constexpr (LO >= HI) {
+		lc_steps<W, HI, HI>(S, C, B, L, N0, N1);
+	} else {
+		if (lo <= LO)
+			lc_steps<W, LO, HI>(S, C, B, L, N0, N1);
+		else
+			lc_dispatch<W, LO + 1, HI>(lo, S, C, B, L, N0, N1);
+	}
+}
+
+template <int W, int P>
+__device__ __forceinline__ void lc_phases(const uint32_t (&S)[W], uint32_t (&C)[W], uint32_t (&B)[W], int &L, int M)
+{
+	if constexpr (P < W) {
+		const int N0 = 32 * P;
+		if (N0 < M) {						/* M is uniform: no divergence */
+			constexpr int HI = (P + 1 < W) ? P + 1 : W - 1;
+			/* lowest index (position + 1) that can be non-zero during this phase */
+			int lo_idx = min(N0 - L + 1, L);
+			lo_idx = __reduce_min_sync(0xffffffffu, lo_idx);
+			lc_dispatch<W, 0, HI>(lo_idx >> 5, S, C, B, L, N0, min(M, N0 + 32));
+			lc_phases<W, P + 1>(S, C, B, L, M);
+		}
+	}
+}
+
+template <int W>
+__global__ void __launch_bounds__(LC_THREADS)
+lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
+	      long long *__restrict__ st)
+{
+	__shared__ unsigned int cls[7];
+	const int64_t s = blockIdx.x;
+	if (threadIdx.x < 7)
+		cls[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int M = (int) P.lc_M;
+	/* whole warps stay alive (the window bound is a warp reduction); surplus lanes redo the last block */
+	const int64_t blk_raw = (int64_t) blockIdx.y * LC_THREADS + threadIdx.x;
+	const int64_t blk = min(blk_raw, P.lc_N - 1);
+	{
+		const int64_t start = blk * M;
+		uint32_t S[W], C[W], B[W];
+#pragma unroll
+		for (int i = 0; i < W; i++) {
+			uint32_t v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * i - 1);
+			int valid = M + 1 - 32 * i;
+			if (valid < 32)
+				v &= mask_below((uint32_t) (valid > 0 ? valid : 0));
+			S[i] = v;
+			C[i] = 0;
+			B[i] = 0;
+		}
+		C[0] = 0x40000000u;
+		B[0] = 0x80000000u;
+		int L = 0;
+		lc_phases<W, 0>(S, C, B, L, M);
+		if (blk_raw < P.lc_N)
+			atomicAdd(&cls[class_lut[L]], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 7 && cls[threadIdx.x])
+		atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
+			  (unsigned long long) cls[threadIdx.x]);
+}
+
 /* any M up to 5000: the same recurrence with the arrays in (L1-resident) local memory */
 #define LC_MAXW 160
 __global__ void __launch_bounds__(LC_THREADS)
@@ -144,7 +249,7 @@ cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_c
 	dim3 grid((unsigned) L.nstreams, (unsigned) ((P.lc_N + LC_THREADS - 1) / LC_THREADS));
 	const int W = (int) ((P.lc_M + 1 + 31) >> 5);
 	if (W <= 16)
-		lc_kernel_reg<16><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		lc_kernel_win<16><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
 	else if (W <= 24)
 		lc_kernel_reg<24><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
 	else if (W <= 32)

@@ -20,7 +20,8 @@
  */
 #include "common.cuh"
 
-#define PAT_THREADS 256
+#define PAT_THREADS 256		/* nonoverlapping: 2 KiB histograms, many CTAs per SM */
+#define HIST_THREADS 1024	/* cyclic histogram: 128 KiB per CTA = one CTA per SM, so make it 32 warps */
 
 /* 32 bits starting at cyclic bit position pos (0 <= pos < n + 64), stream length n bits */
 __device__ __forceinline__ uint32_t cyc32(const uint32_t *__restrict__ w, int64_t pos, int64_t n)
@@ -92,7 +93,7 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 	__syncthreads();
 	unsigned long long t = 0;
 	if (threadIdx.x == 0)
-		for (int i = 0; i < PAT_THREADS / 32; i++)
+		for (int i = 0; i < HIST_THREADS / 32; i++)
 			t += scratch[i];
 	return t;
 }
@@ -100,25 +101,25 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 /*
  * apen_hist layout per stream: [2^(apen_m+1) bins of level apen_m+1][2^apen_m bins of level apen_m]
  */
-__global__ void __launch_bounds__(PAT_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS)
 cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
 		   uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ debug_hist, int debug_bits)
 {
 	extern __shared__ uint32_t hist[];
-	__shared__ unsigned long long red[PAT_THREADS / 32];
+	__shared__ unsigned long long red[HIST_THREADS / 32];
 	const int64_t s = blockIdx.x;
 	const uint32_t slice = blockIdx.y;
 	const int H = debug_hist ? debug_bits : P.hist_bits;
 	const int sb = debug_hist ? (H > 15 ? H - 15 : 0) : P.hist_slice_bits;
 	const int B = H - sb;					/* local histogram bits */
 	const uint32_t lmask = (1u << B) - 1u;
-	for (int i = threadIdx.x; i < (1 << B); i += PAT_THREADS)
+	for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
 		hist[i] = 0;
 	__syncthreads();
 	const uint32_t *__restrict__ w = in + s * P.pitch_words;
 	const int64_t n = P.n;
 	const int64_t groups = (n + 31) >> 5;
-	for (int64_t g = threadIdx.x; g < groups; g += PAT_THREADS) {
+	for (int64_t g = threadIdx.x; g < groups; g += HIST_THREADS) {
 		const int64_t j0 = g * 32;
 		uint32_t cur, nxt;
 		if (j0 + 64 <= n) {
@@ -141,7 +142,7 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 	__syncthreads();
 	if (debug_hist) {
 		uint32_t *o = debug_hist + ((size_t) slice << B);
-		for (int i = threadIdx.x; i < (1 << B); i += PAT_THREADS)
+		for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
 			o[i] = hist[i];
 		return;
 	}
@@ -160,7 +161,7 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 		if (is_serial || is_apen) {
 			unsigned long long sq = 0, lin = 0;
 			const unsigned long long base = (unsigned long long) slice << b;
-			for (int i = threadIdx.x; i < nb; i += PAT_THREADS) {
+			for (int i = threadIdx.x; i < nb; i += HIST_THREADS) {
 				unsigned long long c = hist[i];
 				sq += c * c;
 				lin += (base + i) * c;
@@ -180,7 +181,7 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 			if (is_apen) {
 				uint32_t *dst = apen_hist + s * ((size_t) 3 << am) + (lvl == am + 1 ? 0 : ((size_t) 2 << am))
 						+ ((size_t) slice << b);
-				for (int i = threadIdx.x; i < nb; i += PAT_THREADS)
+				for (int i = threadIdx.x; i < nb; i += HIST_THREADS)
 					dst[i] = hist[i];
 			}
 		}
@@ -188,7 +189,7 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 			break;
 		/* fold to the next level in place: new[i] = old[2i] + old[2i+1] */
 		const int half = nb >> 1;
-		for (int c0 = 0; c0 < max(half, 1); c0 += PAT_THREADS) {
+		for (int c0 = 0; c0 < max(half, 1); c0 += HIST_THREADS) {
 			int i = c0 + threadIdx.x;
 			uint32_t v = 0;
 			if (i < half)
@@ -211,7 +212,7 @@ cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_a
 	if (e != cudaSuccess)
 		return e;
 	dim3 grid((unsigned) L.nstreams, 1u << P.hist_slice_bits);
-	cyclic_hist_kernel<<<grid, PAT_THREADS, smem, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, nullptr, 0);
+	cyclic_hist_kernel<<<grid, HIST_THREADS, smem, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, nullptr, 0);
 	return cudaGetLastError();
 }
 
@@ -225,7 +226,7 @@ cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64
 	if (e != cudaSuccess)
 		return e;
 	dim3 grid(1, 1u << sb);
-	cyclic_hist_kernel<<<grid, PAT_THREADS, smem, L.stream>>>(P, L.d_in + stream_index * P.pitch_words, nullptr,
+	cyclic_hist_kernel<<<grid, HIST_THREADS, smem, L.stream>>>(P, L.d_in + stream_index * P.pitch_words, nullptr,
 								  nullptr, d_out, bits);
 	return cudaGetLastError();
 }
