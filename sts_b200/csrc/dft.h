@@ -10,8 +10,12 @@ struct DftPlan {
 	const double2 *th;	/* exp(-2 pi i 1024 e / N), e < max(1, N / 1024) */
 	const double2 *p1;	/* exp(-2 pi i k1 / n), k1 < N1 */
 	const double2 *p2;	/* exp(-2 pi i N1 k2 / n), k2 < N2 */
-	const double2 *tw8;	/* [7][8]:  exp(-2 pi i k r / 64),  r = 1..7, k < 8  (radix-8 pass with Ns = 8) */
-	const double2 *tw64;	/* [7][64]: exp(-2 pi i k r / 512), r = 1..7, k < 64 (radix-8 pass with Ns = 64) */
-	const double2 *tw2d;	/* [512][1024]: exp(-2 pi i k1 j2 / N) for the n = 2^20 kernels, else NULL */
+	/* tables of the n = 2^20 kernels (k_dft_fast.cu, N = 256 x 2048), NULL otherwise */
+	const double2 *q_twA;	/* [15][16]:  exp(-2 pi i k r / 256),  r = 1..15, k < 16  (radix-16 pass, Ns = 16) */
+	const double2 *q_twB;	/* [7][256]:  exp(-2 pi i j r / 2048), r = 1..7,  j < 256 (radix-8 pass, Ns = 256) */
+	const double2 *q_e1;	/* [16][2048]: exp(-2 pi i j2 t / N) */
+	const double2 *q_e2;	/* [2048]: exp(-2 pi i 16 j2 / N) */
+	const double2 *q_p1;	/* [256]:  exp(-2 pi i k1 / n) */
+	const double2 *q_p2;	/* [2048]: exp(-2 pi i 256 k2 / n) */
 	double T;		/* sqrt(log(20) * n), discreteFourierTransform.c:142 */
 };

@@ -405,24 +405,26 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(upload(&d, th.data(), th.size()), "upload(fft th)"); D.th = d; ctx->dft_tabs[2] = d;
 		CKC(upload(&d, p1.data(), p1.size()), "upload(fft p1)"); D.p1 = d; ctx->dft_tabs[3] = d;
 		CKC(upload(&d, p2.data(), p2.size()), "upload(fft p2)"); D.p2 = d; ctx->dft_tabs[4] = d;
-		{
-			std::vector<double2> t8(7 * 8), t64(7 * 64);
-			for (int r = 1; r < 8; r++) {
-				for (int k = 0; k < 8; k++) t8[(r - 1) * 8 + k] = unit_root(k * r, 64);
-				for (int k = 0; k < 64; k++) t64[(r - 1) * 64 + k] = unit_root(k * r, 512);
-			}
-			CKC(upload(&d, t8.data(), t8.size()), "upload(fft tw8)"); D.tw8 = d; ctx->dft_tabs[5] = d;
-			CKC(upload(&d, t64.data(), t64.size()), "upload(fft tw64)"); D.tw64 = d; ctx->dft_tabs[6] = d;
-			D.tw2d = nullptr;
-			if (D.logN1 == 9 && D.logN2 == 10) {
-				std::vector<double2> t2((size_t) N);
-				for (int k1 = 0; k1 < N1; k1++)
-					for (int j2 = 0; j2 < N2; j2++)
-						t2[(size_t) k1 * N2 + j2] = unit_root((long double) (((int64_t) k1 * j2) % N), (long double) N);
-				CKC(upload(&d, t2.data(), t2.size()), "upload(fft tw2d)"); D.tw2d = d; ctx->dft_tabs[7] = d;
-			}
+		D.q_twA = D.q_twB = D.q_e1 = D.q_e2 = D.q_p1 = D.q_p2 = nullptr;
+		if (D.logN1 == 9 && D.logN2 == 10) {				/* n = 2^20: k_dft_fast.cu */
+			std::vector<double2> tA(15 * 16), tB(7 * 256), e1(16 * 2048), e2(2048), q1(256), q2(2048);
+			for (int r = 1; r < 16; r++)
+				for (int k = 0; k < 16; k++) tA[(r - 1) * 16 + k] = unit_root(k * r, 256);
+			for (int r = 1; r < 8; r++)
+				for (int j = 0; j < 256; j++) tB[(r - 1) * 256 + j] = unit_root(j * r, 2048);
+			for (int t = 0; t < 16; t++)
+				for (int j2 = 0; j2 < 2048; j2++) e1[t * 2048 + j2] = unit_root((long double) j2 * t, (long double) N);
+			for (int j2 = 0; j2 < 2048; j2++) e2[j2] = unit_root((long double) 16 * j2, (long double) N);
+			for (int k = 0; k < 256; k++) q1[k] = unit_root(k, (long double) n);
+			for (int k = 0; k < 2048; k++) q2[k] = unit_root((long double) 256 * k, (long double) n);
+			CKC(upload(&d, tA.data(), tA.size()), "upload(fft twA)"); D.q_twA = d; ctx->dft_tabs[5] = d;
+			CKC(upload(&d, tB.data(), tB.size()), "upload(fft twB)"); D.q_twB = d; ctx->dft_tabs[6] = d;
+			CKC(upload(&d, e1.data(), e1.size()), "upload(fft e1)"); D.q_e1 = d; ctx->dft_tabs[7] = d;
+			CKC(upload(&d, e2.data(), e2.size()), "upload(fft e2)"); D.q_e2 = d; ctx->dft_tabs[8] = d;
+			CKC(upload(&d, q1.data(), q1.size()), "upload(fft q1)"); D.q_p1 = d; ctx->dft_tabs[9] = d;
+			CKC(upload(&d, q2.data(), q2.size()), "upload(fft q2)"); D.q_p2 = d; ctx->dft_tabs[10] = d;
 		}
-		int64_t chunk = 16;
+		int64_t chunk = 32;
 		const char *envc = getenv("STSGPU_DFT_CHUNK");
 		if (envc && atoi(envc) > 0) chunk = atoi(envc);
 		if (chunk > B) chunk = B;
@@ -457,7 +459,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 	cudaFreeHost(ctx->h_pv); cudaFreeHost(ctx->h_st); cudaFreeHost(ctx->h_w);
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_apen_hist); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab);
 	cudaFree(ctx->d_dft_work); cudaFree(ctx->d_debug);
-	for (int i = 0; i < 8; i++) cudaFree(ctx->dft_tabs[i]);
+	for (int i = 0; i < 11; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
 	for (int i = 0; i < STS_AUX_STREAMS; i++) {
 		if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);

@@ -33,7 +33,7 @@ struct stsgpu_ctx {
 	uint8_t *d_class_lut = nullptr;
 	double *d_log2tab = nullptr;
 	double2 *d_dft_work = nullptr;
-	double2 *dft_tabs[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	double2 *dft_tabs[11] = { nullptr };
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
 

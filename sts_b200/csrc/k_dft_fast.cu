@@ -1,173 +1,226 @@
 /*
- * k_dft_fast.cu - the DFT test's four-step FFT specialised for n = 2^20 (N = 2^19 = 512 x 1024), the
- * stream length of the headline benchmark.  Same algorithm and same tables as k_dft.cu (which stays
- * as the generic power-of-two path); here every size is a compile-time constant so the index
- * arithmetic folds away, every table is laid out so that a warp's lookups are contiguous (the LSU
- * wavefront count, not FP64, bounded the first version), each CTA is 256 threads with <= 85 registers (3 CTAs per SM), and the
- * real-FFT post pass handles bins q and N - q together:
- *     A = (Z_q + conj Z_{N-q}) / 2,  B = -(i/2) W_n^q (Z_q - conj Z_{N-q})
- *     X_q = A + B,   X_{N-q} = conj(A - B)
- * and compares squared moduli with T^2 (falling back to the reference's sqrt form only inside a
+ * k_dft_fast.cu - the DFT test's four-step FFT specialised for n = 2^20 (N = n/2 = 2^19 complex
+ * points), the stream length of the headline benchmark.  k_dft.cu stays as the generic
+ * power-of-two path.
+ *
+ * The first version (512 x 1024, radix 8) was bound by the LSU wavefront pipe: six shared-memory
+ * exchanges per point plus scattered twiddle lookups.  This one is built to move less:
+ *
+ *   N = 256 x 2048.  Sixteen points per thread (radix 16 = 4 x 4 in registers) so the columns need
+ *   ONE exchange (16 x 16) and the rows TWO (16 x 16 x 8); every table is laid out so that a warp's
+ *   lookups are contiguous.
+ *
+ *   dft_cols16 : 16 adjacent columns j2 per CTA (one packed input word per row j1), 16 threads per
+ *                column.  C[k1][j2] = sum_j1 z[2048 j1 + j2] W_256^(j1 k1), times W_N^(j2 k1)
+ *                (one table value per thread, then powers of W_N^(16 j2) by repeated multiply),
+ *                stored as Y[k1][j2] in 256-byte runs.
+ *   dft_rows16 : rows (a, 256 - a) per CTA.  Bins q = a + 256 k2 and N - q = (256 - a) +
+ *                256 (2047 - k2) are partners of the real-FFT post pass
+ *                    X_q = (Z_q + conj Z_{N-q})/2 - (i/2) W_n^q (Z_q - conj Z_{N-q});
+ *                in the last (radix 8) pass thread u takes butterfly u of row a and butterfly
+ *                255 - u of row b, whose outputs are exactly each other's partners, so the post pass
+ *                and the |X| < T count run on registers and nothing but the count leaves the CTA.
+ *                Rows 0 and 128 are their own partners and finish through shared memory.
+ *
+ * Moduli are compared squared against T^2 (falling back to the reference's sqrt form only inside a
  * 1e-10 relative band around T, where the north star allows N_1 to differ anyway).
+ *
+ * Per stream: 8 MiB written + 8 MiB read of Y (HBM/L2), three shared-memory exchanges, about
+ * 80 FP64 instructions per complex point.
  */
 #include "common.cuh"
 #include "dft.h"
 #include "dft_math.cuh"
 
-#define FN1 512
-#define FN2 1024
-#define FCW 4			/* columns per CTA in the column pass */
-#define ROWLEN (FN2 + FN2 / 8 + 1)
+#define QN1 256
+#define QN2 2048
+#define QCW 16				/* columns per CTA in the column pass */
+#define QROW (QN2 + QN2 / 16)		/* padded row: one spare element per 16 */
 
-__global__ void __launch_bounds__(256, 3)
-dft_cols_fast(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
+__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
+
+/* 16-point DFT in registers, natural order in and out: j = j0 + 4 j1, k = k1 + 4 k0 */
+__device__ __forceinline__ void bfly16(double2 *v)
 {
-	extern __shared__ double2 buf[];			/* [padi(512)][4] */
-	const int c = threadIdx.x & 3, t = threadIdx.x >> 2;	/* t < 64 */
-	const int j2 = blockIdx.y * FCW + c;
-	const uint32_t *__restrict__ w = in + (stream0 + blockIdx.x) * P.pitch_words + (j2 >> 4);
-	double2 *__restrict__ Ys = Y + (int64_t) blockIdx.x * ((int64_t) FN1 * FN2);
-	const int sh = 30 - ((2 * j2) & 31);
-	double2 v[8];
-
-	/* pass 0 (Ns = 1): z[1024 j1 + j2] straight from the packed bits, j1 = t + 64 r */
+	const double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, r2 = 0.70710678118654752440;
+	double2 a[16];
 #pragma unroll
-	for (int r = 0; r < 8; r++) {
-		const uint32_t two = (ldw(w, 64 * (t + 64 * r)) >> sh) & 3u;
-		v[r] = make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
+	for (int j0 = 0; j0 < 4; j0++) {
+		double2 t[4] = { v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12] };
+		bfly<4>(t);
+#pragma unroll
+		for (int k1 = 0; k1 < 4; k1++)
+			a[j0 * 4 + k1] = t[k1];
 	}
-	bfly<8>(v);
+	/* times W_16^(j0 k1) */
+	a[5] = cmul(a[5], make_double2(c8, -s8));			/* W^1 */
+	a[6] = make_double2(r2 * (a[6].x + a[6].y), r2 * (a[6].y - a[6].x));	/* W^2 */
+	a[7] = cmul(a[7], make_double2(s8, -c8));			/* W^3 */
+	a[9] = make_double2(r2 * (a[9].x + a[9].y), r2 * (a[9].y - a[9].x));	/* W^2 */
+	a[10] = cmi(a[10]);						/* W^4 = -i */
+	a[11] = make_double2(r2 * (a[11].y - a[11].x), -r2 * (a[11].x + a[11].y));	/* W^6 */
+	a[13] = cmul(a[13], make_double2(s8, -c8));			/* W^3 */
+	a[14] = make_double2(r2 * (a[14].y - a[14].x), -r2 * (a[14].x + a[14].y));	/* W^6 */
+	a[15] = cmul(a[15], make_double2(-c8, s8));			/* W^9 */
 #pragma unroll
-	for (int r = 0; r < 8; r++)
-		buf[padi(8 * t + r) * FCW + c] = v[r];
-	__syncthreads();
-
-	/* pass 1 (Ns = 8) */
-	{
+	for (int k1 = 0; k1 < 4; k1++) {
+		double2 t[4] = { a[k1], a[4 + k1], a[8 + k1], a[12 + k1] };
+		bfly<4>(t);
 #pragma unroll
-		for (int r = 0; r < 8; r++)
-			v[r] = buf[padi(t + 64 * r) * FCW + c];
-		const int k = t & 7;
-#pragma unroll
-		for (int r = 1; r < 8; r++)
-			v[r] = cmul(v[r], __ldg(D.tw8 + (r - 1) * 8 + k));
-		bfly<8>(v);
-		__syncthreads();
-		const int base = (t - k) * 8 + k;
-#pragma unroll
-		for (int r = 0; r < 8; r++)
-			buf[padi(base + 8 * r) * FCW + c] = v[r];
-		__syncthreads();
-	}
-
-	/* pass 2 (Ns = 64): output index k1 = t + 64 r, times W_N^(j2 k1), to Y[k1][j2] */
-#pragma unroll
-	for (int r = 0; r < 8; r++)
-		v[r] = buf[padi(t + 64 * r) * FCW + c];
-#pragma unroll
-	for (int r = 1; r < 8; r++)
-		v[r] = cmul(v[r], __ldg(D.tw64 + (r - 1) * 64 + t));
-	bfly<8>(v);
-#pragma unroll
-	for (int r = 0; r < 8; r++) {
-		Ys[(t + 64 * r) * FN2 + j2] = v[r];	/* the W_N^(j2 k1) factor is applied by the row pass */
+		for (int k0 = 0; k0 < 4; k0++)
+			v[k1 + 4 * k0] = t[k0];
 	}
 }
 
-__global__ void __launch_bounds__(256, 3)
-dft_rows_fast(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256, 2)
+dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
-	extern __shared__ double2 buf[];			/* [2][ROWLEN] */
+	extern __shared__ double2 buf[];			/* [256][16] */
+	const int c = threadIdx.x & 15, t = threadIdx.x >> 4;	/* t < 16 */
+	const int j2 = blockIdx.y * QCW + c;
+	const uint32_t *__restrict__ w = in + (stream0 + blockIdx.x) * P.pitch_words + blockIdx.y;
+	double2 *__restrict__ Ys = Y + (int64_t) blockIdx.x * ((int64_t) QN1 * QN2);
+	const int sh = 30 - 2 * c;
+	double2 v[16];
+
+	/* pass 0 (Ns = 1): z[2048 j1 + j2] straight from the packed bits, j1 = t + 16 r */
+#pragma unroll
+	for (int r = 0; r < 16; r++) {
+		const uint32_t two = (ldw(w, 128 * (t + 16 * r)) >> sh) & 3u;
+		v[r] = make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
+	}
+	bfly16(v);
+#pragma unroll
+	for (int r = 0; r < 16; r++)
+		buf[(16 * t + r) * QCW + c] = v[r];
+	__syncthreads();
+
+	/* pass 1 (Ns = 16): k = t, outputs k1 = t + 16 r */
+	v[0] = buf[t * QCW + c];
+#pragma unroll
+	for (int r = 1; r < 16; r++)
+		v[r] = cmul(buf[(t + 16 * r) * QCW + c], __ldg(D.q_twA + (r - 1) * 16 + t));
+	bfly16(v);
+	/* times W_N^(j2 k1) = W_N^(j2 t) (W_N^(16 j2))^r */
+	double2 tw = __ldg(D.q_e1 + t * QN2 + j2);
+	const double2 step = __ldg(D.q_e2 + j2);
+#pragma unroll
+	for (int r = 0; r < 16; r++) {
+		Ys[(t + 16 * r) * QN2 + j2] = cmul(v[r], tw);
+		tw = cmul(tw, step);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* X_q and X_{N-q} from Z_q = zq and Z_{N-q} = zp; wq = exp(-2 pi i q / n); returns how many of the two lie below T */
+__device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double2 wq, double T, double T2, bool both)
+{
+	const double2 sum = make_double2(zq.x + zp.x, zq.y - zp.y);	/* Z_q + conj Z_{N-q} */
+	const double2 dif = make_double2(zq.x - zp.x, zq.y + zp.y);	/* Z_q - conj Z_{N-q} */
+	const double2 wd = cmul(wq, dif);
+	const double ar = sum.x + wd.y, ai = sum.y - wd.x;		/* 2 X_q */
+	const double br = sum.x - wd.y, bi = sum.y + wd.x;		/* 2 conj X_{N-q} */
+	const double m2a = 0.25 * (ar * ar + ai * ai), m2b = 0.25 * (br * br + bi * bi);
+	bool below_a = m2a < T2, below_b = m2b < T2;
+	if (fabs(m2a - T2) < 1e-10 * T2)
+		below_a = sqrt(0.25 * ar * ar + 0.25 * ai * ai) < T;
+	if (fabs(m2b - T2) < 1e-10 * T2)
+		below_b = sqrt(0.25 * br * br + 0.25 * bi * bi) < T;
+	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256, 2)
+dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
+{
+	extern __shared__ double2 buf[];			/* [2][QROW] */
 	__shared__ unsigned int cnt_s;
-	const double2 *__restrict__ Ys = Y + (int64_t) blockIdx.x * ((int64_t) FN1 * FN2);
-	const int pi = blockIdx.y;				/* row pair (pi, 512 - pi), pi = 0 .. 256 */
-	const int k1a = pi, k1b = (FN1 - pi) & (FN1 - 1);
-	const bool self = (k1a == k1b);
+	const double2 *__restrict__ Ys = Y + (int64_t) blockIdx.x * ((int64_t) QN1 * QN2);
+	const int ra = blockIdx.y, rb = (QN1 - ra) & (QN1 - 1);	/* row pair, ra = 0 .. 128 */
+	const bool self = (ra == rb);
 	const int rho = threadIdx.x >> 7, t = threadIdx.x & 127;
 	const bool active = (rho == 0) || !self;
-	const double2 *__restrict__ src = Ys + (rho ? k1b : k1a) * FN2;
-	const double2 *__restrict__ twr = D.tw2d + (rho ? k1b : k1a) * FN2;
-	double2 *row = buf + rho * ROWLEN;
+	double2 *row = buf + rho * QROW;
 	if (threadIdx.x == 0)
 		cnt_s = 0;
-	double2 v[8];
+	double2 v[16];
 
-	/* pass 0 (Ns = 1) */
+	/* pass 0 (Ns = 1): inputs t + 128 r, outputs 16 t + r */
 	if (active) {
+		const double2 *__restrict__ src = Ys + (rho ? rb : ra) * QN2;
 #pragma unroll
-		for (int r = 0; r < 8; r++)
-			v[r] = cmul(src[t + 128 * r], __ldg(twr + t + 128 * r));	/* times W_N^(j2 k1) */
-		bfly<8>(v);
+		for (int r = 0; r < 16; r++)
+			v[r] = src[t + 128 * r];
+		bfly16(v);
 #pragma unroll
-		for (int r = 0; r < 8; r++)
-			row[padi(8 * t + r)] = v[r];
+		for (int r = 0; r < 16; r++)
+			row[pad16(16 * t + r)] = v[r];
 	}
 	__syncthreads();
-	/* pass 1 (Ns = 8) and pass 2 (Ns = 64) */
-#pragma unroll
-	for (int pass = 1; pass <= 2; pass++) {
-		const int Ns = (pass == 1) ? 8 : 64;
-		const int k = t & (Ns - 1);
+	/* pass 1 (Ns = 16): k = t mod 16, outputs 16 (t - k) + k + 16 r */
+	{
+		const int k = t & 15;
 		if (active) {
+			v[0] = row[pad16(t)];
 #pragma unroll
-			for (int r = 0; r < 8; r++)
-				v[r] = row[padi(t + 128 * r)];
-			const double2 *__restrict__ tw = (pass == 1) ? D.tw8 : D.tw64;
-#pragma unroll
-			for (int r = 1; r < 8; r++)
-				v[r] = cmul(v[r], __ldg(tw + (r - 1) * Ns + k));
-			bfly<8>(v);
+			for (int r = 1; r < 16; r++)
+				v[r] = cmul(row[pad16(t + 128 * r)], __ldg(D.q_twA + (r - 1) * 16 + k));
+			bfly16(v);
 		}
 		__syncthreads();
 		if (active) {
-			const int base = (t - k) * 8 + k;
+			const int base = 16 * (t - k) + k;
 #pragma unroll
-			for (int r = 0; r < 8; r++)
-				row[padi(base + r * Ns)] = v[r];
+			for (int r = 0; r < 16; r++)
+				row[pad16(base + 16 * r)] = v[r];
 		}
 		__syncthreads();
 	}
-	/* pass 3 (radix 2, Ns = 512): in place, natural order */
-	if (active) {
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const int j = t + 128 * u;
-			const double2 a = row[padi(j)];
-			const double2 b = cmul(row[padi(j + 512)], __ldg(D.wm + j));
-			row[padi(j)] = cadd(a, b);
-			row[padi(j + 512)] = csub(a, b);
-		}
-	}
-	__syncthreads();
-
-	/* post pass: pairs (q, N - q), q = k1a + 512 k2 in row a, partner in row b */
-	const double2 *ra = buf, *rb = self ? buf : buf + ROWLEN;
+	/* pass 2 (radix 8, Ns = 256): butterfly j reads j + 256 r and yields Z[k2 = j + 256 r] */
 	const double T2 = D.T * D.T;
-	const double2 w1 = __ldg(D.p1 + k1a);
+	const double2 w1 = __ldg(D.q_p1 + ra);			/* exp(-2 pi i ra / n) */
 	unsigned int cnt = 0;
+	if (!self) {
+		const int ja = threadIdx.x, jb = 255 - threadIdx.x;
+		double2 za[8], zb[8];
+		za[0] = buf[pad16(ja)];
+		zb[0] = buf[QROW + pad16(jb)];
 #pragma unroll
-	for (int u = 0; u < 4; u++) {
-		const int k2 = threadIdx.x + 256 * u;
-		const int k2p = (k1a == 0) ? ((FN2 - k2) & (FN2 - 1)) : (FN2 - 1 - k2);
-		if (self && k2 > k2p)
-			continue;				/* each unordered pair once */
-		const double2 zq = ra[padi(k2)];
-		const double2 zp = rb[padi(k2p)];
-		const double2 wq = cmul(w1, __ldg(D.p2 + k2));	/* exp(-2 pi i q / n) */
-		const double2 sum = make_double2(zq.x + zp.x, zq.y - zp.y);	/* Z_q + conj Z_{N-q} */
-		const double2 dif = make_double2(zq.x - zp.x, zq.y + zp.y);	/* Z_q - conj Z_{N-q} */
-		const double2 wd = cmul(wq, dif);
-		const double ar = sum.x + wd.y, ai = sum.y - wd.x;		/* 2 X_q */
-		const double br = sum.x - wd.y, bi = sum.y + wd.x;		/* 2 conj X_{N-q} */
-		const double m2a = 0.25 * (ar * ar + ai * ai), m2b = 0.25 * (br * br + bi * bi);
-		bool below_a = m2a < T2, below_b = m2b < T2;
-		if (fabs(m2a - T2) < 1e-10 * T2)
-			below_a = sqrt(0.25 * ar * ar + 0.25 * ai * ai) < D.T;
-		if (fabs(m2b - T2) < 1e-10 * T2)
-			below_b = sqrt(0.25 * br * br + 0.25 * bi * bi) < D.T;
-		cnt += below_a ? 1u : 0u;
-		if (!(self && k2 == k2p))			/* q = 0 and q = N/2 are their own partners */
-			cnt += below_b ? 1u : 0u;
+		for (int r = 1; r < 8; r++) {
+			za[r] = cmul(buf[pad16(ja + 256 * r)], __ldg(D.q_twB + (r - 1) * 256 + ja));
+			zb[r] = cmul(buf[QROW + pad16(jb + 256 * r)], __ldg(D.q_twB + (r - 1) * 256 + jb));
+		}
+		bfly<8>(za);
+		bfly<8>(zb);
+		/* bin q = ra + 256 (ja + 256 r); its partner N - q = rb + 256 (jb + 256 (7 - r)) */
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			const double2 wq = cmul(w1, __ldg(D.q_p2 + ja + 256 * r));
+			cnt += post_pair(za[r], zb[7 - r], wq, D.T, T2, true);
+		}
+	} else {
+		const int ja = threadIdx.x;
+		double2 za[8];
+		za[0] = buf[pad16(ja)];
+#pragma unroll
+		for (int r = 1; r < 8; r++)
+			za[r] = cmul(buf[pad16(ja + 256 * r)], __ldg(D.q_twB + (r - 1) * 256 + ja));
+		bfly<8>(za);
+		__syncthreads();
+#pragma unroll
+		for (int r = 0; r < 8; r++)
+			buf[pad16(ja + 256 * r)] = za[r];
+		__syncthreads();
+		/* row 0: N - q = 256 (2048 - k2); row 128: N - q = 128 + 256 (2047 - k2); each unordered pair once */
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			const int k2 = ja + 256 * r;
+			const int k2p = (ra == 0) ? ((QN2 - k2) & (QN2 - 1)) : (QN2 - 1 - k2);
+			if (k2 > k2p)
+				continue;
+			const double2 wq = cmul(w1, __ldg(D.q_p2 + k2));
+			cnt += post_pair(buf[pad16(k2)], buf[pad16(k2p)], wq, D.T, T2, k2 != k2p);
+		}
 	}
 	cnt = (unsigned int) warp_sum((int) cnt);
 	if ((threadIdx.x & 31) == 0 && cnt)
@@ -180,19 +233,19 @@ dft_rows_fast(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *
 
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams)
 {
-	const size_t smem1 = (size_t) (FN1 + FN1 / 8 + 1) * FCW * sizeof(double2);
-	const size_t smem2 = (size_t) 2 * ROWLEN * sizeof(double2);
+	const size_t smem1 = (size_t) QN1 * QCW * sizeof(double2);
+	const size_t smem2 = (size_t) 2 * QROW * sizeof(double2);
 	cudaError_t e;
-	e = cudaFuncSetAttribute(dft_cols_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
+	e = cudaFuncSetAttribute(dft_cols16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(dft_rows_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
+	e = cudaFuncSetAttribute(dft_rows16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
 	if (e != cudaSuccess) return e;
 	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams) {
 		const int64_t cs = (L.nstreams - s0 < work_streams) ? L.nstreams - s0 : work_streams;
-		dim3 g1((unsigned) cs, FN2 / FCW);
-		dft_cols_fast<<<g1, 256, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
-		dim3 g2((unsigned) cs, FN1 / 2 + 1);
-		dft_rows_fast<<<g2, 256, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		dim3 g1((unsigned) cs, QN2 / QCW);
+		dft_cols16<<<g1, 256, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		dim3 g2((unsigned) cs, QN1 / 2 + 1);
+		dft_rows16<<<g2, 256, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
 	}
 	return cudaGetLastError();
 }
