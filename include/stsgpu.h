@@ -91,7 +91,7 @@ typedef struct stsgpu_params {
 	int64_t n;			/* tp.n: bits per stream (default 1048576) */
 	int64_t max_streams;		/* capacity of one submit (streams per batch) */
 	uint32_t test_mask;		/* bit t set <=> state->testVector[t] (1..15) */
-	int32_t reserved0;
+	int32_t pipeline_depth;		/* batches that may be in flight at once: 0 or 1 = one (default), max 4 */
 	int64_t block_frequency_M;	/* tp.blockFrequencyBlockLength      (16384) */
 	int32_t non_overlapping_m;	/* tp.nonOverlappingTemplateLength   (9) */
 	int32_t overlapping_m;		/* tp.overlappingTemplateLength      (9) */
@@ -162,20 +162,28 @@ int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out);
 int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams, int64_t first_iteration);
 
 /*
- * Same, for input that is already resident in the engine's device input buffer (filled by
- * stsgpu_generate_lcg or stsgpu_upload): no H2D inside.
+ * Same, for input that is already resident in the device input buffer of the batch slot this
+ * submit uses (filled by stsgpu_generate_lcg or stsgpu_upload since the previous submit, or left
+ * there by the submit `pipeline_depth` batches ago): no H2D inside.
  */
 int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration);
 
 /* copy raw bytes into the device input buffer without running the tests */
 int stsgpu_upload(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams);
 
-/* block until the submitted batch is done and its records are in host memory */
+/*
+ * Block until the OLDEST submitted batch is done and its records are in host memory.  Up to
+ * `pipeline_depth` batches may be submitted before the first wait; they complete in submit order,
+ * and the copies of one batch overlap the kernels of the others.  (The reference overlaps the same
+ * way with -T threads: one reads the next stream while the others iterate, utilities.c:1601-1625.)
+ */
 int stsgpu_wait(stsgpu_ctx *ctx);
+/* batches submitted and not yet waited for */
+int stsgpu_pending(const stsgpu_ctx *ctx);
 
 /*
  * Records of the last completed batch: pointers to engine-owned pinned host arrays of
- * nstreams*npv doubles, nstreams*nst int64 and nstreams*nw uint32, valid until the next submit.
+ * nstreams*npv doubles, nstreams*nst int64 and nstreams*nw uint32, valid until the next stsgpu_wait.
  */
 int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first_iteration,
 		   const double **pvals, const int64_t **istats, const uint32_t **wcount);
@@ -217,7 +225,8 @@ int stsgpu_comm_barrier(stsgpu_ctx *ctx);
 /*
  * Per-kernel-group CUDA events are always recorded on the stream each group is launched on.
  * on = 1 additionally serialises all groups on one stream, so that each duration is that of the
- * group running alone (otherwise groups overlap on four streams and durations include sharing).
+ * group running alone (otherwise groups overlap on two streams per batch slot and durations include
+ * sharing).  Kernel and batch times refer to the batch returned by the last stsgpu_wait.
  */
 int stsgpu_set_profiling(stsgpu_ctx *ctx, int on);
 /* kernels launched by the last submit; name/ms for entry i (ms valid after stsgpu_wait) */

@@ -19,7 +19,7 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
 EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_submit",
-           "stsgpu_submit_resident", "stsgpu_upload", "stsgpu_wait", "stsgpu_results", "stsgpu_generate_lcg",
+           "stsgpu_submit_resident", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_set_profiling",
            "stsgpu_kernel_count", "stsgpu_kernel_info", "stsgpu_last_batch_ms", "stsgpu_launch_count",
@@ -32,7 +32,7 @@ class EngineError(RuntimeError):
 
 class Params(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n", C.c_int64), ("max_streams", C.c_int64),
-                ("test_mask", C.c_uint32), ("reserved0", C.c_int32), ("block_frequency_M", C.c_int64),
+                ("test_mask", C.c_uint32), ("pipeline_depth", C.c_int32), ("block_frequency_M", C.c_int64),
                 ("non_overlapping_m", C.c_int32), ("overlapping_m", C.c_int32), ("apen_m", C.c_int32),
                 ("serial_m", C.c_int32), ("linear_complexity_M", C.c_int64)]
 
@@ -77,6 +77,7 @@ def load_library():
     lib.stsgpu_submit_resident.argtypes = [vp, i64, i64]
     lib.stsgpu_upload.argtypes = [vp, vp, i64]
     lib.stsgpu_wait.argtypes = [vp]
+    lib.stsgpu_pending.argtypes = [vp]
     lib.stsgpu_results.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.stsgpu_generate_lcg.argtypes = [vp, i64, i64]
     lib.stsgpu_download_input.argtypes = [vp, vp, i64]
@@ -174,7 +175,7 @@ class Engine:
             assert raw.dtype == np.uint8 and raw.flags["C_CONTIGUOUS"]
             assert raw.size >= nstreams * self.params.n // 8
             ptr = raw.ctypes.data
-            self._keep = raw
+            self._keep = (getattr(self, "_keep", ()) + (raw,))[-4:]	# borrowed until the batch's wait
         else:
             ptr = raw
         self._ck(self.lib.stsgpu_submit(self.h, ptr, nstreams, first_iteration), "submit")
@@ -184,11 +185,14 @@ class Engine:
 
     def upload(self, raw, nstreams):
         raw = np.ascontiguousarray(raw, dtype=np.uint8)
-        self._keep = raw
+        self._keep = (getattr(self, "_keep", ()) + (raw,))[-4:]
         self._ck(self.lib.stsgpu_upload(self.h, raw.ctypes.data, nstreams), "upload")
 
     def wait(self):
         self._ck(self.lib.stsgpu_wait(self.h), "wait")
+
+    def pending(self):
+        return self.lib.stsgpu_pending(self.h)
 
     def results(self, copy=True):
         ns, first = C.c_int64(), C.c_int64()

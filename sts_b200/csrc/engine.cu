@@ -2,12 +2,13 @@
  * engine.cu - the C ABI of include/stsgpu.h: context, parameter checks that mirror the X_init()
  * self-disable rules, device buffers, batch submission and result records.
  *
- * HBM layout of one context (n = 2^20, capacity B streams):
+ * HBM layout of one context (n = 2^20, capacity B streams), per batch slot (engine.h):
  *   d_in        B x pitch bytes   raw file bytes of every stream, pitch = 128-byte multiple >= n/8 + 16
  *   d_pv/d_st/d_w                 B records (188 doubles, 176 int64, 1184 uint32 at defaults)
  *   d_apen_hist B x 3 * 2^apen_m  uint32, the two ApEn histograms in index order
  *   d_dft_work  chunk x n/2       double2, the four-step FFT intermediate (8 MiB per stream)
- *   constant tables               templates, LC class LUT, log2 table (Universal), FFT twiddles
+ * and once per context: templates, LC class LUT, log2 table (Universal), FFT twiddles.
+ * `pipeline_depth` slots (default 1) are used round robin so that consecutive batches overlap.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -340,19 +341,38 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 					   "stsgpu_create");                                                      \
 		}                                                                                                 \
 	} while (0)
-	CKC(cudaMalloc((void **) &ctx->d_in, ctx->in_bytes), "cudaMalloc(input)");
-	CKC(cudaMemset(ctx->d_in, 0, ctx->in_bytes), "cudaMemset(input)");
-	CKC(cudaMalloc((void **) &ctx->d_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMalloc(pvals)");
-	CKC(cudaMalloc((void **) &ctx->d_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMalloc(istats)");
-	CKC(cudaMalloc((void **) &ctx->d_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMalloc(wcount)");
-	CKC(cudaMallocHost((void **) &ctx->h_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMallocHost(pvals)");
-	CKC(cudaMallocHost((void **) &ctx->h_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMallocHost(istats)");
-	CKC(cudaMallocHost((void **) &ctx->h_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMallocHost(wcount)");
+	ctx->nslots = p->pipeline_depth > 1 ? p->pipeline_depth : 1;
+	if (ctx->nslots > STS_MAX_SLOTS) ctx->nslots = STS_MAX_SLOTS;
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);		/* lo = least urgent, hi = most urgent */
+	for (int i = 0; i < ctx->nslots; i++) {
+		Slot &S = ctx->slots[i];
+		CKC(cudaMalloc((void **) &S.d_in, ctx->in_bytes), "cudaMalloc(input)");
+		CKC(cudaMemset(S.d_in, 0, ctx->in_bytes), "cudaMemset(input)");
+		CKC(cudaMalloc((void **) &S.d_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMalloc(pvals)");
+		CKC(cudaMalloc((void **) &S.d_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMalloc(istats)");
+		CKC(cudaMalloc((void **) &S.d_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMalloc(wcount)");
+		CKC(cudaMallocHost((void **) &S.h_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMallocHost(pvals)");
+		CKC(cudaMallocHost((void **) &S.h_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMallocHost(istats)");
+		CKC(cudaMallocHost((void **) &S.h_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMallocHost(wcount)");
+		if (want_apen)
+			CKC(cudaMalloc((void **) &S.d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
+			    "cudaMalloc(apen histograms)");
+		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreate(&S.ev_start), "cudaEventCreate");
+		CKC(cudaEventCreate(&S.ev_end), "cudaEventCreate");
+		for (int k = 0; k < STS_MAX_KERNELS; k++) {
+			CKC(cudaEventCreate(&S.k_ev0[k]), "cudaEventCreate");
+			CKC(cudaEventCreate(&S.k_ev1[k]), "cudaEventCreate");
+		}
+	}
+	CKC(cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking), "cudaStreamCreate");
 	if (!tmpl.empty())
 		CKC(upload(&ctx->d_templates, tmpl.data(), tmpl.size()), "upload(templates)");
-	if (want_apen)
-		CKC(cudaMalloc((void **) &ctx->d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
-		    "cudaMalloc(apen histograms)");
 	if (en & (1u << STSGPU_TEST_LINEARCOMPLEXITY)) {
 		/*
 		 * class of every possible L (linearComplexity.c:356-377), evaluated on the host by the
@@ -429,19 +449,8 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		if (envc && atoi(envc) > 0) chunk = atoi(envc);
 		if (chunk > B) chunk = B;
 		ctx->dft_chunk = chunk;
-		CKC(cudaMalloc((void **) &ctx->d_dft_work, (size_t) chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
-	}
-	CKC(cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking), "cudaStreamCreate");
-	for (int i = 0; i < STS_AUX_STREAMS; i++) {
-		CKC(cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking), "cudaStreamCreate");
-		CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming), "cudaEventCreate");
-	}
-	CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
-	CKC(cudaEventCreate(&ctx->ev_start), "cudaEventCreate");
-	CKC(cudaEventCreate(&ctx->ev_end), "cudaEventCreate");
-	for (int i = 0; i < STS_MAX_KERNELS; i++) {
-		CKC(cudaEventCreate(&ctx->k_ev0[i]), "cudaEventCreate");
-		CKC(cudaEventCreate(&ctx->k_ev1[i]), "cudaEventCreate");
+		for (int i = 0; i < ctx->nslots; i++)
+			CKC(cudaMalloc((void **) &ctx->slots[i].d_dft_work, (size_t) chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
 	}
 #undef CKC
 	*out = ctx;
@@ -453,25 +462,28 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 	if (ctx == NULL)
 		return;
 	cudaSetDevice(ctx->device);
-	if (ctx->s_main) cudaStreamSynchronize(ctx->s_main);
+	cudaDeviceSynchronize();
 	stsgpu_comm_destroy_internal(ctx);
-	cudaFree(ctx->d_in); cudaFree(ctx->d_pv); cudaFree(ctx->d_st); cudaFree(ctx->d_w);
-	cudaFreeHost(ctx->h_pv); cudaFreeHost(ctx->h_st); cudaFreeHost(ctx->h_w);
-	cudaFree(ctx->d_templates); cudaFree(ctx->d_apen_hist); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab);
-	cudaFree(ctx->d_dft_work); cudaFree(ctx->d_debug);
+	for (int i = 0; i < STS_MAX_SLOTS; i++) {
+		Slot &S = ctx->slots[i];
+		cudaFree(S.d_in); cudaFree(S.d_pv); cudaFree(S.d_st); cudaFree(S.d_w);
+		cudaFreeHost(S.h_pv); cudaFreeHost(S.h_st); cudaFreeHost(S.h_w);
+		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work);
+		if (S.s_light) cudaStreamDestroy(S.s_light);
+		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
+		if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+		if (S.ev_join) cudaEventDestroy(S.ev_join);
+		if (S.ev_done) cudaEventDestroy(S.ev_done);
+		if (S.ev_start) cudaEventDestroy(S.ev_start);
+		if (S.ev_end) cudaEventDestroy(S.ev_end);
+		for (int k = 0; k < STS_MAX_KERNELS; k++) {
+			if (S.k_ev0[k]) cudaEventDestroy(S.k_ev0[k]);
+			if (S.k_ev1[k]) cudaEventDestroy(S.k_ev1[k]);
+		}
+	}
+	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
 	for (int i = 0; i < 11; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
-	for (int i = 0; i < STS_AUX_STREAMS; i++) {
-		if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
-		if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
-	}
-	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-	if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-	if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
-	for (int i = 0; i < STS_MAX_KERNELS; i++) {
-		if (ctx->k_ev0[i]) cudaEventDestroy(ctx->k_ev0[i]);
-		if (ctx->k_ev1[i]) cudaEventDestroy(ctx->k_ev1[i]);
-	}
 	delete ctx;
 }
 
@@ -486,39 +498,42 @@ extern "C" int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out)
 /* ------------------------------------------------------------------------------------------ */
 struct Group {
 	const char *name;
-	int stream;		/* -1: main, else aux index */
+	bool heavy;		/* true: throughput-bound, low-priority stream */
 };
 
-static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
+static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_iteration)
 {
 	const DevParams &P = ctx->P;
 	const stsgpu_layout &lay = ctx->lay;
-	cudaStream_t sm = ctx->s_main;
-	CK(cudaMemsetAsync(ctx->d_st, 0, (size_t) nstreams * lay.nst * sizeof(long long), sm));
-	CK(cudaEventRecord(ctx->ev_start, sm));
-	ctx->nkernels = 0;
+	cudaStream_t sl = S.s_light;
+	CK(cudaMemsetAsync(S.d_st, 0, (size_t) nstreams * lay.nst * sizeof(long long), sl));
+	CK(cudaEventRecord(S.ev_start, sl));
+	S.nkernels = 0;
 	const bool prof = ctx->profiling;
 
 	LaunchCtx L;
-	L.d_in = ctx->d_in; L.d_pv = ctx->d_pv; L.d_st = ctx->d_st; L.d_w = ctx->d_w;
+	L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
 	L.nstreams = nstreams; L.num_sms = ctx->num_sms;
 
 	if (!prof) {
-		CK(cudaEventRecord(ctx->ev_fork, sm));
-		for (int i = 0; i < STS_AUX_STREAMS; i++)
-			CK(cudaStreamWaitEvent(ctx->s_aux[i], ctx->ev_fork, 0));
+		CK(cudaEventRecord(S.ev_fork, sl));
+		CK(cudaStreamWaitEvent(S.s_heavy, S.ev_fork, 0));
 	}
-	/* kernel groups; without profiling they run concurrently on four streams */
-	enum { G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_PATTERN, G_UNIVERSAL, G_LC, G_DFT, G_COUNT };
+	/*
+	 * Kernel groups.  Without profiling the throughput-bound groups run on the slot's low-priority
+	 * stream and the latency-bound ones on its high-priority stream, so that the small kernels get
+	 * SM slots as soon as they free up instead of queueing behind the big grids.
+	 */
+	enum { G_DFT, G_LC, G_PATTERN, G_UNIVERSAL, G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_COUNT };
 	static const Group groups[G_COUNT] = {
-		{ "scan(freq,cusum,runs,excursions)", -1 }, { "blocks(blockfreq,longestrun,overlapping)", -1 },
-		{ "rank", -1 }, { "nonoverlapping", -1 }, { "pattern(serial,apen)", 2 }, { "universal", 2 },
-		{ "linear_complexity", 0 }, { "dft", 1 },
+		{ "dft", true }, { "linear_complexity", true }, { "pattern(serial,apen)", true },
+		{ "universal", false }, { "scan(freq,cusum,runs,excursions)", false },
+		{ "blocks(blockfreq,longestrun,overlapping)", false }, { "rank", false }, { "nonoverlapping", false },
 	};
 	for (int g = 0; g < G_COUNT; g++) {
-		L.stream = (prof || groups[g].stream < 0) ? sm : ctx->s_aux[groups[g].stream];
-		const int slot = ctx->nkernels;
-		CK(cudaEventRecord(ctx->k_ev0[slot], L.stream));
+		L.stream = (prof || !groups[g].heavy) ? sl : S.s_heavy;
+		const int slot = S.nkernels;
+		CK(cudaEventRecord(S.k_ev0[slot], L.stream));
 		cudaError_t e = cudaSuccess;
 		int64_t launched = 0;
 		switch (g) {
@@ -526,11 +541,11 @@ static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 		case G_BLOCKS: e = launch_blocks(P, L); launched = 3; break;
 		case G_RANK: e = launch_rank(P, L); launched = 1; break;
 		case G_NONOV: e = launch_nonoverlapping(P, L, ctx->d_templates); launched = 1; break;
-		case G_PATTERN: e = launch_pattern(P, L, ctx->d_apen_hist); launched = 1; break;
+		case G_PATTERN: e = launch_pattern(P, L, S.d_apen_hist); launched = 1; break;
 		case G_UNIVERSAL: e = launch_universal(P, L, ctx->d_log2tab); launched = 1; break;
 		case G_LC: e = launch_lc(P, L, ctx->d_class_lut); launched = 1; break;
 		case G_DFT:
-			e = launch_dft(P, L, ctx->dft, ctx->d_dft_work, ctx->dft_chunk);
+			e = launch_dft(P, L, ctx->dft, S.d_dft_work, ctx->dft_chunk);
 			launched = (P.enabled & (1u << STSGPU_TEST_DFT)) ? 2 * ((nstreams + ctx->dft_chunk - 1) / ctx->dft_chunk) : 0;
 			break;
 		}
@@ -539,43 +554,43 @@ static int run_tests(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 			return STSGPU_E_CUDA;
 		}
 		ctx->launches += launched;
-		CK(cudaEventRecord(ctx->k_ev1[slot], L.stream));
-		ctx->k_name[slot] = groups[g].name;
-		ctx->nkernels++;
+		CK(cudaEventRecord(S.k_ev1[slot], L.stream));
+		S.k_name[slot] = groups[g].name;
+		S.nkernels++;
 	}
 	if (!prof) {
-		for (int i = 0; i < STS_AUX_STREAMS; i++) {
-			CK(cudaEventRecord(ctx->ev_join[i], ctx->s_aux[i]));
-			CK(cudaStreamWaitEvent(sm, ctx->ev_join[i], 0));
-		}
+		CK(cudaEventRecord(S.ev_join, S.s_heavy));
+		CK(cudaStreamWaitEvent(sl, S.ev_join, 0));
 	}
-	L.stream = sm;
+	L.stream = sl;
 	{
-		const int slot = ctx->nkernels;
-		CK(cudaEventRecord(ctx->k_ev0[slot], sm));
-		cudaError_t e = launch_tails(P, ctx->K, L, ctx->d_apen_hist);
+		const int slot = S.nkernels;
+		CK(cudaEventRecord(S.k_ev0[slot], sl));
+		cudaError_t e = launch_tails(P, ctx->K, L, S.d_apen_hist);
 		if (e != cudaSuccess) {
 			set_err(ctx, "tails", e);
 			return STSGPU_E_CUDA;
 		}
 		ctx->launches += 1;
-		CK(cudaEventRecord(ctx->k_ev1[slot], sm));
-		ctx->k_name[slot] = "tails(p-values)";
-		ctx->nkernels++;
+		CK(cudaEventRecord(S.k_ev1[slot], sl));
+		S.k_name[slot] = "tails(p-values)";
+		S.nkernels++;
 	}
-	CK(cudaEventRecord(ctx->ev_end, sm));
-	CK(cudaMemcpyAsync(ctx->h_pv, ctx->d_pv, (size_t) nstreams * lay.npv * sizeof(double), cudaMemcpyDeviceToHost, sm));
-	CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sm));
+	CK(cudaEventRecord(S.ev_end, sl));
+	CK(cudaMemcpyAsync(S.h_pv, S.d_pv, (size_t) nstreams * lay.npv * sizeof(double), cudaMemcpyDeviceToHost, sl));
+	CK(cudaMemcpyAsync(S.h_st, S.d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sl));
 	if (lay.nw)
-		CK(cudaMemcpyAsync(ctx->h_w, ctx->d_w, (size_t) nstreams * lay.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, sm));
-	ctx->cur_nstreams = nstreams;
-	ctx->cur_first = first_iteration;
-	ctx->in_flight = true;
-	ctx->have_results = false;
+		CK(cudaMemcpyAsync(S.h_w, S.d_w, (size_t) nstreams * lay.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl));
+	CK(cudaEventRecord(S.ev_done, sl));
+	S.nstreams = nstreams;
+	S.first = first_iteration;
+	S.in_flight = true;
+	ctx->submit_seq++;
 	return STSGPU_OK;
 }
 
-static int check_batch(stsgpu_ctx *ctx, int64_t nstreams)
+/* the slot the next submit / upload / generate works on; fails while that slot is still in flight */
+static int next_slot(stsgpu_ctx *ctx, int64_t nstreams, Slot **out)
 {
 	if (ctx == NULL)
 		return STSGPU_E_INVAL;
@@ -583,23 +598,27 @@ static int check_batch(stsgpu_ctx *ctx, int64_t nstreams)
 		snprintf(ctx->err, sizeof(ctx->err), "nstreams %lld outside 1..max_streams", (long long) nstreams);
 		return STSGPU_E_RANGE;
 	}
-	if (ctx->in_flight) {
-		snprintf(ctx->err, sizeof(ctx->err), "a batch is still in flight: call stsgpu_wait first");
+	Slot &S = ctx->slots[ctx->submit_seq % ctx->nslots];
+	if (S.in_flight) {
+		snprintf(ctx->err, sizeof(ctx->err), "%d batches are in flight (pipeline_depth): call stsgpu_wait first",
+			 ctx->nslots);
 		return STSGPU_E_STATE;
 	}
 	if (cudaSetDevice(ctx->device) != cudaSuccess)
 		return STSGPU_E_CUDA;
+	*out = &S;
 	return STSGPU_OK;
 }
 
 extern "C" int stsgpu_upload(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams)
 {
-	int rc = check_batch(ctx, nstreams);
+	Slot *S;
+	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
 	if (raw == NULL) return STSGPU_E_INVAL;
 	const size_t row = (size_t) (ctx->P.n / 8);
-	CK(cudaMemcpy2DAsync(ctx->d_in, (size_t) ctx->P.pitch_words * 4, raw, row, row, (size_t) nstreams,
-			     cudaMemcpyHostToDevice, ctx->s_main));
+	CK(cudaMemcpy2DAsync(S->d_in, (size_t) ctx->P.pitch_words * 4, raw, row, row, (size_t) nstreams,
+			     cudaMemcpyHostToDevice, S->s_light));
 	return STSGPU_OK;
 }
 
@@ -607,32 +626,43 @@ extern "C" int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstrea
 {
 	int rc = stsgpu_upload(ctx, raw, nstreams);
 	if (rc) return rc;
-	return run_tests(ctx, nstreams, first_iteration);
+	return run_tests(ctx, ctx->slots[ctx->submit_seq % ctx->nslots], nstreams, first_iteration);
 }
 
 extern "C" int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
 {
-	int rc = check_batch(ctx, nstreams);
+	Slot *S;
+	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
-	return run_tests(ctx, nstreams, first_iteration);
+	return run_tests(ctx, *S, nstreams, first_iteration);
 }
 
 extern "C" int stsgpu_wait(stsgpu_ctx *ctx)
 {
 	if (ctx == NULL)
 		return STSGPU_E_INVAL;
-	if (!ctx->in_flight) {
+	const int idx = (int) (ctx->wait_seq % ctx->nslots);
+	Slot &S = ctx->slots[idx];
+	if (!S.in_flight || ctx->wait_seq >= ctx->submit_seq) {
 		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_wait without a submitted batch");
 		return STSGPU_E_STATE;
 	}
 	cudaSetDevice(ctx->device);
-	ctx->in_flight = false;
-	CK(cudaStreamSynchronize(ctx->s_main));
-	for (int i = 0; i < STS_AUX_STREAMS; i++)
-		CK(cudaStreamSynchronize(ctx->s_aux[i]));
+	S.in_flight = false;
+	ctx->wait_seq++;
+	CK(cudaEventSynchronize(S.ev_done));
 	CK(cudaGetLastError());
+	ctx->last_done = idx;
+	ctx->d_pv = S.d_pv;
+	ctx->h_pv = S.h_pv;
+	ctx->cur_nstreams = S.nstreams;
 	ctx->have_results = true;
 	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_pending(const stsgpu_ctx *ctx)
+{
+	return ctx ? (int) (ctx->submit_seq - ctx->wait_seq) : 0;
 }
 
 extern "C" int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first_iteration, const double **pvals,
@@ -644,20 +674,22 @@ extern "C" int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first
 		snprintf(ctx->err, sizeof(ctx->err), "no completed batch");
 		return STSGPU_E_STATE;
 	}
-	if (nstreams) *nstreams = ctx->cur_nstreams;
-	if (first_iteration) *first_iteration = ctx->cur_first;
-	if (pvals) *pvals = ctx->h_pv;
-	if (istats) *istats = (const int64_t *) ctx->h_st;
-	if (wcount) *wcount = ctx->h_w;
+	const Slot &S = ctx->slots[ctx->last_done];
+	if (nstreams) *nstreams = S.nstreams;
+	if (first_iteration) *first_iteration = S.first;
+	if (pvals) *pvals = S.h_pv;
+	if (istats) *istats = (const int64_t *) S.h_st;
+	if (wcount) *wcount = S.h_w;
 	return STSGPU_OK;
 }
 
 extern "C" int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_t nstreams)
 {
-	int rc = check_batch(ctx, nstreams);
+	Slot *S;
+	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
 	if (first_stream < 0) return STSGPU_E_INVAL;
-	cudaError_t e = launch_lcg(ctx->P, ctx->d_in, first_stream, nstreams, ctx->s_main);
+	cudaError_t e = launch_lcg(ctx->P, S->d_in, first_stream, nstreams, S->s_light);
 	if (e != cudaSuccess) {
 		set_err(ctx, "lcg", e);
 		return STSGPU_E_CUDA;
@@ -668,13 +700,14 @@ extern "C" int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_
 
 extern "C" int stsgpu_download_input(stsgpu_ctx *ctx, uint8_t *raw, int64_t nstreams)
 {
-	int rc = check_batch(ctx, nstreams);
+	Slot *S;
+	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
 	if (raw == NULL) return STSGPU_E_INVAL;
 	const size_t row = (size_t) (ctx->P.n / 8);
-	CK(cudaMemcpy2DAsync(raw, row, ctx->d_in, (size_t) ctx->P.pitch_words * 4, row, (size_t) nstreams,
-			     cudaMemcpyDeviceToHost, ctx->s_main));
-	CK(cudaStreamSynchronize(ctx->s_main));
+	CK(cudaMemcpy2DAsync(raw, row, S->d_in, (size_t) ctx->P.pitch_words * 4, row, (size_t) nstreams,
+			     cudaMemcpyDeviceToHost, S->s_light));
+	CK(cudaStreamSynchronize(S->s_light));
 	return STSGPU_OK;
 }
 
@@ -698,14 +731,19 @@ extern "C" int stsgpu_set_profiling(stsgpu_ctx *ctx, int on)
 	ctx->profiling = on != 0;
 	return STSGPU_OK;
 }
-extern "C" int stsgpu_kernel_count(const stsgpu_ctx *ctx) { return ctx ? ctx->nkernels : 0; }
+extern "C" int stsgpu_kernel_count(const stsgpu_ctx *ctx)
+{
+	return (ctx && ctx->last_done >= 0) ? ctx->slots[ctx->last_done].nkernels : 0;
+}
 extern "C" int stsgpu_kernel_info(stsgpu_ctx *ctx, int i, const char **name, float *ms)
 {
-	if (ctx == NULL || i < 0 || i >= ctx->nkernels) return STSGPU_E_RANGE;
-	if (name) *name = ctx->k_name[i];
+	if (ctx == NULL || ctx->last_done < 0) return STSGPU_E_RANGE;
+	Slot &S = ctx->slots[ctx->last_done];
+	if (i < 0 || i >= S.nkernels) return STSGPU_E_RANGE;
+	if (name) *name = S.k_name[i];
 	if (ms) {
 		*ms = 0.f;
-		CK(cudaEventElapsedTime(ms, ctx->k_ev0[i], ctx->k_ev1[i]));
+		CK(cudaEventElapsedTime(ms, S.k_ev0[i], S.k_ev1[i]));
 	}
 	return STSGPU_OK;
 }
@@ -713,20 +751,28 @@ extern "C" int stsgpu_last_batch_ms(stsgpu_ctx *ctx, float *ms)
 {
 	if (ctx == NULL || ms == NULL) return STSGPU_E_INVAL;
 	if (!ctx->have_results) return STSGPU_E_STATE;
-	CK(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_end));
+	Slot &S = ctx->slots[ctx->last_done];
+	CK(cudaEventElapsedTime(ms, S.ev_start, S.ev_end));
 	return STSGPU_OK;
 }
 extern "C" int64_t stsgpu_launch_count(const stsgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int stsgpu_debug_pattern_histogram(stsgpu_ctx *ctx, int64_t s, int bits, uint32_t *hist)
 {
-	int rc = check_batch(ctx, 1);
-	if (rc) return rc;
+	if (ctx == NULL) return STSGPU_E_INVAL;
+	if (ctx->submit_seq != ctx->wait_seq) {
+		snprintf(ctx->err, sizeof(ctx->err), "debug histogram needs an idle engine");
+		return STSGPU_E_STATE;
+	}
 	if (hist == NULL || bits < 1 || bits > 21 || s < 0 || s >= ctx->prm.max_streams) return STSGPU_E_INVAL;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return STSGPU_E_CUDA;
+	/* input of the last completed batch, or of the slot about to be submitted when nothing ran yet */
+	Slot &S = ctx->slots[ctx->last_done >= 0 ? ctx->last_done : (int) (ctx->submit_seq % ctx->nslots)];
+	CK(cudaStreamSynchronize(S.s_light));
 	if (ctx->d_debug == NULL)
 		CK(cudaMalloc((void **) &ctx->d_debug, sizeof(uint32_t) << 21));
 	LaunchCtx L;
-	L.stream = ctx->s_main; L.d_in = ctx->d_in; L.d_pv = ctx->d_pv; L.d_st = ctx->d_st; L.d_w = ctx->d_w;
+	L.stream = ctx->s_main; L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
 	L.nstreams = 1; L.num_sms = ctx->num_sms;
 	cudaError_t e = launch_debug_histogram(ctx->P, L, s, bits, ctx->d_debug);
 	if (e != cudaSuccess) {

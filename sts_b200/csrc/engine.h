@@ -5,7 +5,32 @@
 #include "tails.h"
 #include "dft.h"
 
-#define STS_AUX_STREAMS 3
+#define STS_MAX_SLOTS 4
+
+/*
+ * One batch in flight.  A context owns `nslots` of these and uses them round robin, so that the
+ * host-to-device copy, the kernels and the record copy of consecutive batches overlap.  Each slot
+ * has two streams: `s_light` (high priority: copies, the latency-bound kernels, the tails) and
+ * `s_heavy` (low priority: pattern histograms, linear complexity, DFT), forked and joined by events.
+ */
+struct Slot {
+	uint32_t *d_in = nullptr;
+	double *d_pv = nullptr;
+	long long *d_st = nullptr;
+	uint32_t *d_w = nullptr;
+	double *h_pv = nullptr;
+	long long *h_st = nullptr;
+	uint32_t *h_w = nullptr;
+	uint32_t *d_apen_hist = nullptr;
+	double2 *d_dft_work = nullptr;
+	cudaStream_t s_light = nullptr, s_heavy = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_end = nullptr, ev_done = nullptr;
+	int nkernels = 0;
+	const char *k_name[STS_MAX_KERNELS] = { nullptr };
+	cudaEvent_t k_ev0[STS_MAX_KERNELS] = { nullptr }, k_ev1[STS_MAX_KERNELS] = { nullptr };
+	int64_t nstreams = 0, first = 0;
+	bool in_flight = false;
+};
 
 struct stsgpu_ctx {
 	stsgpu_params prm;
@@ -15,35 +40,28 @@ struct stsgpu_ctx {
 	DftPlan dft;
 	int device = 0, num_sms = 0;
 
-	cudaStream_t s_main = nullptr, s_aux[STS_AUX_STREAMS] = { nullptr, nullptr, nullptr };
-	cudaEvent_t ev_fork = nullptr, ev_join[STS_AUX_STREAMS] = { nullptr, nullptr, nullptr };
-	cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+	int nslots = 2;
+	Slot slots[STS_MAX_SLOTS];
+	uint64_t submit_seq = 0;	/* the next submit / upload / generate uses slot submit_seq % nslots */
+	uint64_t wait_seq = 0;		/* the next wait completes slot wait_seq % nslots */
+	int last_done = -1;		/* slot whose records stsgpu_results() returns */
 
-	uint32_t *d_in = nullptr;
+	cudaStream_t s_main = nullptr;	/* collectives and debug helpers */
 	size_t in_bytes = 0;
-	double *d_pv = nullptr;
-	long long *d_st = nullptr;
-	uint32_t *d_w = nullptr;
-	double *h_pv = nullptr;
-	long long *h_st = nullptr;
-	uint32_t *h_w = nullptr;
+
+	/* views of the last completed slot (comm.cu gathers from these) */
+	double *d_pv = nullptr, *h_pv = nullptr;
+	int64_t cur_nstreams = 0;
+	bool have_results = false;
 
 	uint32_t *d_templates = nullptr;
-	uint32_t *d_apen_hist = nullptr;
 	uint8_t *d_class_lut = nullptr;
 	double *d_log2tab = nullptr;
-	double2 *d_dft_work = nullptr;
 	double2 *dft_tabs[11] = { nullptr };
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
 
-	int64_t cur_nstreams = 0, cur_first = 0;
-	bool in_flight = false, have_results = false;
-
 	bool profiling = false;
-	int nkernels = 0;
-	const char *k_name[STS_MAX_KERNELS] = { nullptr };
-	cudaEvent_t k_ev0[STS_MAX_KERNELS] = { nullptr }, k_ev1[STS_MAX_KERNELS] = { nullptr };
 	int64_t launches = 0;
 
 	/* NCCL (comm.cu) */

@@ -111,6 +111,7 @@ sts_init(struct sts_state *s)
 	p.apen_m = (int32_t) s->tp.approximateEntropyBlockLength;
 	p.serial_m = (int32_t) s->tp.serialBlockLength;
 	p.linear_complexity_M = s->tp.linearComplexitySequenceLength;
+	p.pipeline_depth = 2;					/* sts_invokeTestSuite keeps two batches in flight */
 	if ((s->tp.n % 8) != 0)					/* parse_args.c:939 */
 		sts_err(1, __func__, "bitcount(n): %ld must be a multiple of 8", s->tp.n);
 	int rc = stsgpu_create(&p, &s->engine);
@@ -259,7 +260,8 @@ read_streams(struct sts_state *s, uint8_t *dst, long streams)
 /*
  * invokeTestSuite(): replaces the pthread pool of handleFileBasedBitStreams/testBits.  Seek rule of
  * the reference (utilities.c:1526): job `jobnum` starts at byte jobnum * n * iterations / 8.
- * Double buffered: while the GPU tests batch k, the host reads batch k+1 into the other pinned buffer.
+ * Pipelined two deep: while the GPU tests batch k, the host reads and submits batch k+1 from the other
+ * pinned buffer, then runs the record keeping of batch k.
  */
 void
 sts_invokeTestSuite(struct sts_state *s)
@@ -281,32 +283,40 @@ sts_invokeTestSuite(struct sts_state *s)
 			sts_err(212, __func__, "cannot allocate pinned read buffer of %ld bytes", B * nb);
 	}
 	struct sts_thread_state ts = { 0, s, 0, NULL };
-	long done = 0, cur = 0;
-	long have = read_streams(s, buf[0], B < s->tp.numOfBitStreams ? B : s->tp.numOfBitStreams);
-	while (have > 0) {
-		int rc = stsgpu_submit(s->engine, buf[cur], have, done);
-		if (rc != STSGPU_OK)
-			sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
-		long left = s->tp.numOfBitStreams - done - have;
-		long next = 0;
-		if (left > 0)					/* overlap the next read with the GPU */
-			next = read_streams(s, buf[cur ^ 1], left < B ? left : B);
-		rc = stsgpu_wait(s->engine);
+	const long total = s->tp.numOfBitStreams;
+	long submitted = 0, done = 0;
+	int w = 0, eof = 0;
+	for (;;) {
+		/* keep two batches in flight: the read and the upload of one overlap the kernels of the other */
+		while (stsgpu_pending(s->engine) < 2 && !eof && submitted < total) {
+			const long want = (total - submitted) < B ? (total - submitted) : B;
+			const long have = read_streams(s, buf[w & 1], want);
+			if (have < want)
+				eof = 1;
+			if (have <= 0)
+				break;
+			int rc = stsgpu_submit(s->engine, buf[w & 1], have, submitted);
+			if (rc != STSGPU_OK)
+				sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+			submitted += have;
+			w++;
+		}
+		if (stsgpu_pending(s->engine) == 0)
+			break;
+		int rc = stsgpu_wait(s->engine);
 		if (rc != STSGPU_OK)
 			sts_err(216, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
 		int64_t bn, bf;
 		stsgpu_results(s->engine, &bn, &bf, &s->batch_pvals, NULL, NULL);
 		s->batch_first = (long) bf;
 		s->batch_count = (long) bn;
-		for (long k = 0; k < have; k++) {		/* iteration order: reproducible .pvalues */
+		for (long k = 0; k < (long) bn; k++) {		/* iteration order: reproducible .pvalues */
 			ts.iteration_being_done = done + k;
 			sts_iterate(&ts);
 			if (s->reportCycle > 0 && ((done + k + 1) % s->reportCycle) == 0)
 				printf("Completed %ld iterations of %ld\n", done + k + 1, s->tp.numOfBitStreams);
 		}
-		done += have;
-		have = next;
-		cur ^= 1;
+		done += (long) bn;
 	}
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
 	for (int i = 0; i < 2; i++)

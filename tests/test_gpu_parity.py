@@ -183,6 +183,34 @@ def test_full_batch_properties_and_sampled_parity(sts, oracle):
     assert r.max() <= PV_RTOL
 
 
+def test_pipelined_batches_complete_in_order(sts, oracle):
+    """pipeline_depth = 2: two batches in flight give the records of the same batches run one at a time"""
+    n = 1 << 20
+    raw = oracle.lcg_bytes(20, 6)
+    a, b, c = raw[:2 * n // 8].copy(), raw[2 * n // 8:4 * n // 8].copy(), raw[4 * n // 8:].copy()
+    with sts.Engine(max_streams=2) as one:
+        ref = [one.run(x, 2, 100 + 2 * i) for i, x in enumerate((a, b, c))]
+    with sts.Engine(max_streams=2, pipeline_depth=2) as eng:
+        eng.submit(a, 2, 100)
+        eng.submit(b, 2, 102)
+        assert eng.pending() == 2
+        with pytest.raises(sts.EngineError):
+            eng.submit(c, 2, 104)                            # third batch while two are in flight
+        got = []
+        eng.wait()
+        got.append(eng.results())
+        eng.submit(c, 2, 104)                                # slot of batch a is free again
+        eng.wait()
+        got.append(eng.results())
+        eng.wait()
+        got.append(eng.results())
+        assert eng.pending() == 0
+        with pytest.raises(sts.EngineError):
+            eng.wait()
+    for (pv, st, w), (rpv, rst, rw) in zip(got, ref):
+        assert (pv == rpv).all() and (st == rst).all() and (w == rw).all()
+
+
 def test_partial_test_masks(sts, oracle):
     """state->testVector subsets (the reference's -t flag) change the record layout, not the values"""
     raw = oracle.lcg_bytes(5, 2)
