@@ -444,7 +444,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			CKC(upload(&d, q1.data(), q1.size()), "upload(fft q1)"); D.q_p1 = d; ctx->dft_tabs[9] = d;
 			CKC(upload(&d, q2.data(), q2.size()), "upload(fft q2)"); D.q_p2 = d; ctx->dft_tabs[10] = d;
 		}
-		int64_t chunk = 32;
+		int64_t chunk = 128;
 		const char *envc = getenv("STSGPU_DFT_CHUNK");
 		if (envc && atoi(envc) > 0) chunk = atoi(envc);
 		if (chunk > B) chunk = B;

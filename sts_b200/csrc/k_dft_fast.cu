@@ -32,6 +32,9 @@
 #include "dft.h"
 #include "dft_math.cuh"
 
+#ifndef DFT_MINCTA
+#define DFT_MINCTA 3
+#endif
 #define QN1 256
 #define QN2 2048
 #define QCW 16				/* columns per CTA in the column pass */
@@ -73,7 +76,7 @@ __device__ __forceinline__ void bfly16(double2 *v)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, DFT_MINCTA)
 dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
 	extern __shared__ double2 buf[];			/* [256][16] */
@@ -130,7 +133,7 @@ __device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double
 	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, DFT_MINCTA)
 dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
 	extern __shared__ double2 buf[];			/* [2][QROW] */

@@ -7,17 +7,21 @@
  * lgamma(a) is only ever needed for per-configuration constants a, so the host evaluates it with
  * glibc (as the reference does through cephes.h:33-35) and passes the values in TailConsts.
  *
- * One CTA per stream.
- *   stage 1: one thread per p-value slot (all tests except CumulativeSums and ApproximateEntropy);
- *   stage 2: CumulativeSums (cusum.c:329-370): warps 0/1 evaluate 32 terms of the two series at a
- *            time and add them in the reference's k order;
- *   stage 3: ApproximateEntropy phi (approximateEntropy.c:396-407): the CTA evaluates
- *            C*log(C/n) for 1024 bins at a time, thread 0 adds them in index order.
+ * Three kernels, all latency-bound chains that only pay off when thousands of them run at once:
+ *   tails_slots_kernel : one THREAD per (p-value slot, stream), a warp = one slot of 32 consecutive
+ *            streams, so a warp's lanes run the same cephes loop (igamc with a = 2^15 / 2 for Serial is
+ *            ~1000 dependent divisions; with one CTA per stream it serialised the whole batch);
+ *   tails_cusum_kernel : CumulativeSums (cusum.c:329-370), one warp per (stream, direction): 32 terms
+ *            of the two series at a time, added in the reference's k order;
+ *   tails_apen_kernel  : ApproximateEntropy phi (approximateEntropy.c:396-407), one warp per stream:
+ *            C*log(C/n) for 128 bins at a time, accumulated in index order exactly as the reference's
+ *            sequential loop does, but in parallel (rne_sum.cuh), then igamc.
  */
 #include "common.cuh"
 #include "tails.h"
+#include "rne_sum.cuh"
 
-#define TAIL_THREADS 256
+#define TAIL_THREADS 128
 #define NONP STSGPU_NON_P_VALUE
 
 /* utils/cephes.c:31-32,49-50 */
@@ -117,21 +121,21 @@ __device__ __forceinline__ int test_of_slot(const DevParams &P, int q, int *sub)
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS)
-tails_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ w_all,
-	     const uint32_t *__restrict__ apen_hist, double *__restrict__ pv_all, int64_t nstreams)
+tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ w_all,
+		   double *__restrict__ pv_all, int64_t nstreams)
 {
-	__shared__ double terms[1024];
-	const int64_t s = blockIdx.x;
-	if (s >= nstreams)
+	/* warp -> (slot q, 32 consecutive streams) */
+	const int64_t groups = (nstreams + 31) >> 5;
+	const int64_t gw = (int64_t) blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+	const int q = (int) (gw / groups);
+	const int64_t s = (gw % groups) * 32 + (threadIdx.x & 31);
+	if (q >= P.npv || s >= nstreams)
 		return;
 	long long *st = st_all + s * P.nst;
 	const uint32_t *wc = w_all + s * P.nw;
 	double *pv = pv_all + s * P.npv;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const long long n = P.n;
-
-	/* ---------------- stage 1 ---------------- */
-	for (int q = tid; q < P.npv; q += TAIL_THREADS) {
+	{
 		int sub;
 		const int t = test_of_slot(P, q, &sub);
 		const long long *c = st + P.st_off[t];
@@ -287,8 +291,23 @@ tails_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const ui
 			pv[q] = p;
 	}
 
-	/* ---------------- stage 2: CumulativeSums, cusum.c:353-369 ---------------- */
-	if ((P.enabled & (1u << STSGPU_TEST_CUSUM)) && warp < 2) {
+}
+
+/* CumulativeSums, cusum.c:353-369: one warp per (stream, direction) */
+__global__ void __launch_bounds__(TAIL_THREADS)
+tails_cusum_kernel(DevParams P, TailConsts K, const long long *__restrict__ st_all, double *__restrict__ pv_all,
+		   int64_t nstreams)
+{
+	const int64_t gw = (int64_t) blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+	const int64_t s = gw >> 1;
+	const int warp = (int) (gw & 1);			/* 0: forward, 1: backward */
+	const int lane = threadIdx.x & 31;
+	if (s >= nstreams)
+		return;
+	const long long *st = st_all + s * P.nst;
+	double *pv = pv_all + s * P.npv;
+	const long long n = P.n;
+	{
 		const long long z = st[P.st_off[STSGPU_TEST_CUSUM] + 3 + warp];	/* warp 0: forward, 1: backward */
 		double sum1 = 0.0, sum2 = 0.0;
 		if (z > 0) {
@@ -325,50 +344,77 @@ tails_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const ui
 			pv[P.pv_off[STSGPU_TEST_CUSUM] + warp] = 1.0 - sum1 + sum2;
 	}
 
-	/* ---------------- stage 3: ApproximateEntropy ---------------- */
-	if (P.enabled & (1u << STSGPU_TEST_APEN)) {
-		const int m = P.apen_m;
-		const uint32_t *h = apen_hist + s * ((size_t) 3 << m);
-		double phi[2];
-		for (int r = 0; r < 2; r++) {
-			const uint32_t *hr = (r == 1) ? h : h + ((size_t) 2 << m);	/* r = 0: level m, r = 1: level m+1 */
-			const long long bins = 1LL << (m + r);
-			double sum = 0.0;
-			for (long long base = 0; base < bins; base += 1024) {
-				__syncthreads();
-				for (int i = tid; i < 1024; i += TAIL_THREADS) {
-					double term = 0.0;
-					if (base + i < bins) {
-						uint32_t C = hr[base + i];
-						if (C)
-							term = (double) C * log(C / (double) n);
-					}
-					terms[i] = term;
+}
+
+/* ApproximateEntropy, approximateEntropy.c:396-407 and :230-246: one warp per stream */
+__global__ void __launch_bounds__(TAIL_THREADS)
+tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ apen_hist,
+		  double *__restrict__ pv_all, int64_t nstreams)
+{
+	__shared__ __align__(16) double tbuf[TAIL_THREADS / 32][128];
+	const int64_t s = (int64_t) blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (s >= nstreams)
+		return;
+	double *tb = tbuf[threadIdx.x >> 5];
+	long long *st = st_all + s * P.nst;
+	double *pv = pv_all + s * P.npv;
+	const long long n = P.n;
+	const int m = P.apen_m;
+	const uint32_t *h = apen_hist + s * ((size_t) 3 << m);
+	double phi[2];
+	for (int r = 0; r < 2; r++) {
+		const uint32_t *hr = (r == 1) ? h : h + ((size_t) 2 << m);	/* r = 0: level m, r = 1: level m+1 */
+		const long long bins = 1LL << (m + r);
+		/* every term C*log(C/n) is <= 0: accumulate magnitudes (rounding is symmetric), negate at the end */
+		double mag = 0.0;
+		for (long long base = 0; base < bins; base += 128) {
+			double tm[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const long long i = base + 4 * lane + j;
+				double term = 0.0;
+				if (i < bins) {
+					const uint32_t C = hr[i];
+					if (C)
+						term = (double) C * log(C / (double) n);
 				}
-				__syncthreads();
-				if (tid == 0) {
-					long long lim = bins - base < 1024 ? bins - base : 1024;
-					for (int i = 0; i < lim; i++)
-						sum += terms[i];
-				}
+				tm[j] = -term;
 			}
-			phi[r] = sum / (double) n;
+			const double4 t4 = make_double4(tm[0], tm[1], tm[2], tm[3]);
+			if (!warp_rne_sum128(mag, t4, lane)) {
+				__syncwarp();
+				*(double4 *) (tb + 4 * lane) = t4;
+				__syncwarp();
+#pragma unroll 8
+				for (int j = 0; j < 128; j++)
+					mag += tb[j];
+			}
 		}
-		if (tid == 0) {
-			long long *c = st + P.st_off[STSGPU_TEST_APEN];
-			c[0] = __double_as_longlong(phi[0]);
-			c[1] = __double_as_longlong(phi[1]);
-			double ApEn = phi[0] - phi[1];
-			double chi_squared = 2.0 * n * (K.log2_ - ApEn);
-			pv[P.pv_off[STSGPU_TEST_APEN]] =
-				d_igamc((double) ((long long) 1 << (m - 1)), chi_squared / 2.0, K.lgam_apen);
-		}
+		phi[r] = -mag / (double) n;
+	}
+	if (lane == 0) {
+		long long *c = st + P.st_off[STSGPU_TEST_APEN];
+		c[0] = __double_as_longlong(phi[0]);
+		c[1] = __double_as_longlong(phi[1]);
+		double ApEn = phi[0] - phi[1];
+		double chi_squared = 2.0 * n * (K.log2_ - ApEn);
+		pv[P.pv_off[STSGPU_TEST_APEN]] = d_igamc((double) ((long long) 1 << (m - 1)), chi_squared / 2.0, K.lgam_apen);
 	}
 }
 
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist)
 {
-	tails_kernel<<<(unsigned) L.nstreams, TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_w, d_apen_hist, L.d_pv,
-									   L.nstreams);
+	const int wpb = TAIL_THREADS / 32;
+	const int64_t groups = (L.nstreams + 31) >> 5;
+	const int64_t slot_warps = groups * P.npv;
+	tails_slots_kernel<<<(unsigned) ((slot_warps + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_w, L.d_pv,
+												      L.nstreams);
+	if (P.enabled & (1u << STSGPU_TEST_CUSUM))
+		tails_cusum_kernel<<<(unsigned) ((2 * L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_pv,
+														  L.nstreams);
+	if (P.enabled & (1u << STSGPU_TEST_APEN))
+		tails_apen_kernel<<<(unsigned) ((L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, d_apen_hist,
+													     L.d_pv, L.nstreams);
 	return cudaGetLastError();
 }

@@ -10,14 +10,10 @@
  *     universal.c:327);
  *   - looks the term up in a table log2tab[d] = log(d) / log(2.0) computed ON THE HOST with the
  *     reference's expression and libm, so each addend is the reference's double;
- *   - reproduces the sequential round-to-nearest-even accumulation EXACTLY but in parallel: while
- *     the running sum s stays inside one binade [2^k, 2^(k+1)) it is an integer S in units of
- *     u = 2^(k-52), and adding a term x >= 0 is  S -> S + round(x / u)  where only a tie
- *     (x / u = q + 1/2) depends on the state, through the parity of S.  Every term is therefore a
- *     map  S -> S + (S even ? a0 : a1)  with |a1 - a0| <= 1; these maps are closed under
- *     composition, so 128 terms (4 rows) are composed 4 per lane and then by a 5-step warp
- *     butterfly.  A group that would leave the binade (about 14 of 1010 groups at L = 7), or that
- *     starts below 2^6, is added term by term with DADD in block order instead.
+ *   - reproduces the sequential round-to-nearest-even accumulation EXACTLY but in parallel
+ *     (rne_sum.cuh): 128 terms (4 rows) at a time as composable integer maps; a group that would
+ *     leave the binade of the running sum (about 14 of 1010 groups at L = 7) is added term by term
+ *     with DADD in block order instead.
  *
  * One warp per stream (one CTA = one warp).  The packed stream is staged through shared memory in
  * "super rows" of 32 L words = 1024 blocks with cp.async, double buffered, so DRAM latency is off
@@ -26,6 +22,7 @@
  * Algorithmic bytes: ceil((Q + K) * L / 8) per stream (113120 at L = 7) + the L1/L2-resident table.
  */
 #include "common.cuh"
+#include "rne_sum.cuh"
 
 #define UNI_GROUP 4			/* rows per summation group */
 
@@ -36,49 +33,6 @@ __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gs
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-/* one addend as a map S -> S + (S even ? a0 : a0 + dl) in units of 2^(k-52); needs k >= 6 > exponent(x) + 1 */
-struct RneMap {
-	unsigned long long a0;
-	int dl;
-};
-
-__device__ __forceinline__ RneMap rne_of_term(double x, int k)
-{
-	RneMap f;
-	f.a0 = 0;
-	f.dl = 0;
-	const unsigned long long xb = (unsigned long long) __double_as_longlong(x);
-	if (xb != 0) {
-		const int e = (int) (xb >> 52) - 1023;
-		const unsigned long long M = (xb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
-		int sh = k - e;
-		sh = sh > 62 ? 62 : sh;
-		unsigned long long q = M >> sh;
-		const unsigned long long r = M & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
-		if (r > half) {
-			q++;
-		} else if (r == half) {			/* tie: the result must be even */
-			f.dl = (q & 1ull) ? -1 : 1;
-			q += (q & 1ull);
-		}
-		f.a0 = q;
-	}
-	return f;
-}
-
-/* f first, then g */
-__device__ __forceinline__ RneMap rne_compose(const RneMap &f, const RneMap &g)
-{
-	const unsigned long long f1 = f.a0 + (long long) f.dl;
-	const unsigned long long g1 = g.a0 + (long long) g.dl;
-	const unsigned long long h0 = f.a0 + ((f.a0 & 1ull) ? g1 : g.a0);
-	const unsigned long long h1 = f1 + ((f1 & 1ull) ? g.a0 : g1);
-	RneMap h;
-	h.a0 = h0;
-	h.dl = (int) (long long) (h1 - h0);
-	return h;
-}
 
 __global__ void __launch_bounds__(32)
 universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__restrict__ log2tab,
@@ -166,33 +120,8 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 			if (!testing)
 				continue;
 			/* universal.c:369: sequential accumulation in block order, reproduced exactly */
-			const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
-			const int k = (int) (sb >> 52) - 1023;
-			bool fast = k >= 6;
-			unsigned long long Snew = 0;
-			if (fast) {
-				const double4 ta = *(const double4 *) (tbuf + 4 * lane);
-				RneMap f = rne_of_term(ta.x, k);
-				f = rne_compose(f, rne_of_term(ta.y, k));
-				f = rne_compose(f, rne_of_term(ta.z, k));
-				f = rne_compose(f, rne_of_term(ta.w, k));
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					RneMap g;
-					const uint32_t plo = __shfl_xor_sync(0xffffffffu, (uint32_t) f.a0, o);
-					const uint32_t phi = __shfl_xor_sync(0xffffffffu, (uint32_t) (f.a0 >> 32) | ((uint32_t) (f.dl + 1) << 30), o);
-					g.a0 = ((unsigned long long) (phi & 0x3FFFFFFFu) << 32) | plo;
-					g.dl = (int) (phi >> 30) - 1;
-					f = (lane & o) ? rne_compose(g, f) : rne_compose(f, g);
-				}
-				const unsigned long long S = (sb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
-				Snew = S + ((S & 1ull) ? f.a0 + (long long) f.dl : f.a0);
-				fast = Snew < 0x0020000000000000ull;	/* still inside the binade */
-			}
-			if (fast) {
-				sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) |
-									(Snew & 0x000FFFFFFFFFFFFFull)));
-			} else {
+			const double4 ta = *(const double4 *) (tbuf + 4 * lane);
+			if (!warp_rne_sum128(sum, ta, lane)) {
 #pragma unroll 8
 				for (int j = 0; j < UNI_GROUP * 32; j++)
 					sum += tbuf[j];

@@ -1,0 +1,96 @@
+/*
+ * rne_sum.cuh - exact reproduction of a SEQUENTIAL double-precision sum  s = fl(s + x_i)  of
+ * non-negative terms, evaluated in parallel by a warp.
+ *
+ * The reference adds long lists of terms one after the other (universal.c:369, 128000 terms;
+ * approximateEntropy.c:396-407, 3072 terms) and the rounding of every step depends on the order, so
+ * a tree or an exactly rounded sum gives a different double (FP parity traps).
+ * While the running sum stays inside one binade [2^k, 2^(k+1)) it is an integer S in units of
+ * u = 2^(k-52), and adding x >= 0 is  S -> S + round(x / u)  where only a tie (x / u = q + 1/2)
+ * depends on the state, through the parity of S (round half to even).  Every term is therefore a
+ * map  S -> S + (S even ? a0 : a0 + dl), dl in {-1, 0, 1}; these maps are closed under composition
+ * (after a tie both parities land on an even value), so 128 terms are composed four per lane and
+ * then by a 5-step butterfly.  A group that would leave the binade, or whose terms are not at least
+ * two binades below the sum, is reported back and the caller adds it term by term.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct RneMap {
+	unsigned long long a0;
+	int dl;
+};
+
+/* x >= 0 as a map in units of 2^(k-52); needs k >= exponent(x) + 1 */
+__device__ __forceinline__ RneMap rne_of_term(double x, int k)
+{
+	RneMap f;
+	f.a0 = 0;
+	f.dl = 0;
+	const unsigned long long xb = (unsigned long long) __double_as_longlong(x);
+	if (xb != 0) {
+		const int e = (int) (xb >> 52) - 1023;
+		const unsigned long long M = (xb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+		int sh = k - e;
+		sh = sh > 62 ? 62 : sh;
+		unsigned long long q = M >> sh;
+		const unsigned long long r = M & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+		if (r > half) {
+			q++;
+		} else if (r == half) {			/* tie: the result must be even */
+			f.dl = (q & 1ull) ? -1 : 1;
+			q += (q & 1ull);
+		}
+		f.a0 = q;
+	}
+	return f;
+}
+
+/* f first, then g */
+__device__ __forceinline__ RneMap rne_compose(const RneMap &f, const RneMap &g)
+{
+	const unsigned long long f1 = f.a0 + (long long) f.dl;
+	const unsigned long long g1 = g.a0 + (long long) g.dl;
+	const unsigned long long h0 = f.a0 + ((f.a0 & 1ull) ? g1 : g.a0);
+	const unsigned long long h1 = f1 + ((f1 & 1ull) ? g.a0 : g1);
+	RneMap h;
+	h.a0 = h0;
+	h.dl = (int) (long long) (h1 - h0);
+	return h;
+}
+
+/*
+ * sum += t[0] + ... + t[127] in index order, lane l holding terms 4l .. 4l+3 (all >= 0, sum >= 0,
+ * normal numbers or zero).  Returns true when done exactly on the fast path; false when the caller
+ * has to add the 128 terms one by one (sum untouched).  All lanes hold the same `sum`.
+ */
+__device__ __forceinline__ bool warp_rne_sum128(double &sum, const double4 &t, int lane)
+{
+	const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
+	const int k = (int) (sb >> 52) - 1023;
+	const double tm = fmax(fmax(t.x, t.y), fmax(t.z, t.w));
+	const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int) __double2hiint(tm));
+	const int emax = (int) (hi >> 20) - 1023;
+	if (k < emax + 2 || k < -1000)
+		return false;
+	RneMap f = rne_of_term(t.x, k);
+	f = rne_compose(f, rne_of_term(t.y, k));
+	f = rne_compose(f, rne_of_term(t.z, k));
+	f = rne_compose(f, rne_of_term(t.w, k));
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		RneMap g;
+		const uint32_t plo = __shfl_xor_sync(0xffffffffu, (uint32_t) f.a0, o);
+		const uint32_t phi = __shfl_xor_sync(0xffffffffu, (uint32_t) (f.a0 >> 32) | ((uint32_t) (f.dl + 1) << 30), o);
+		g.a0 = ((unsigned long long) (phi & 0x3FFFFFFFu) << 32) | plo;
+		g.dl = (int) (phi >> 30) - 1;
+		f = (lane & o) ? rne_compose(g, f) : rne_compose(f, g);
+	}
+	const unsigned long long S = (sb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+	const unsigned long long Snew = S + ((S & 1ull) ? f.a0 + (long long) f.dl : f.a0);
+	if (Snew >= 0x0020000000000000ull)		/* would leave the binade */
+		return false;
+	sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) | (Snew & 0x000FFFFFFFFFFFFFull)));
+	return true;
+}
