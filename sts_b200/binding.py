@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBNAME = os.path.join(_HERE, "libstsgpu.so")
+_LIBNAME = os.environ.get("STSGPU_LIB") or os.path.join(_HERE, "libstsgpu.so")	# override: A/B builds of the engine
 
 ALL_TESTS = 0xFFFE
 NON_P_VALUE = -99999999.0

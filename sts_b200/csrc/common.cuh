@@ -109,6 +109,8 @@ __device__ __forceinline__ int warp_scan_incl(int v, int lane)
 /* host-side launch bookkeeping shared by the kernel files */
 struct LaunchCtx {
 	cudaStream_t stream;
+	cudaStream_t stream2;		/* DFT only: odd chunks run here, overlapping the even ones (may equal `stream`) */
+	cudaEvent_t ev2_fork, ev2_join;
 	const uint32_t *d_in;		/* packed input */
 	double *d_pv;
 	long long *d_st;

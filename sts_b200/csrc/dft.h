@@ -17,5 +17,6 @@ struct DftPlan {
 	const double2 *q_e2;	/* [2048]: exp(-2 pi i 16 j2 / N) */
 	const double2 *q_p1;	/* [256]:  exp(-2 pi i k1 / n) */
 	const double2 *q_p2;	/* [2048]: exp(-2 pi i 256 k2 / n) */
+	int dbg;		/* experiment switches (STSGPU_DFT_DBG), 0 in production */
 	double T;		/* sqrt(log(20) * n), discreteFourierTransform.c:142 */
 };

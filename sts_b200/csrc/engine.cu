@@ -360,6 +360,9 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			    "cudaMalloc(apen histograms)");
 		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_heavy2, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_dft_fork, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_dft_join, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming), "cudaEventCreate");
@@ -413,6 +416,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		int cw = 512 / N1 > 8 ? 512 / N1 : 8;
 		if (cw > N2) cw = N2;
 		D.cw = cw;
+		D.dbg = getenv("STSGPU_DFT_DBG") ? atoi(getenv("STSGPU_DFT_DBG")) : 0;
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
 		std::vector<double2> wm(1024), tl(1024), th((size_t) (N >= 1024 ? N / 1024 : 1)), p1(N1), p2(N2);
 		for (int k = 0; k < 1024; k++) { wm[k] = unit_root(k, 1024); tl[k] = unit_root(k, (long double) N); }
@@ -450,7 +454,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		if (chunk > B) chunk = B;
 		ctx->dft_chunk = chunk;
 		for (int i = 0; i < ctx->nslots; i++)
-			CKC(cudaMalloc((void **) &ctx->slots[i].d_dft_work, (size_t) chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
+			CKC(cudaMalloc((void **) &ctx->slots[i].d_dft_work, (size_t) 2 * chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
 	}
 #undef CKC
 	*out = ctx;
@@ -471,6 +475,9 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
 		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
+		if (S.s_heavy2) cudaStreamDestroy(S.s_heavy2);
+		if (S.ev_dft_fork) cudaEventDestroy(S.ev_dft_fork);
+		if (S.ev_dft_join) cudaEventDestroy(S.ev_dft_join);
 		if (S.ev_fork) cudaEventDestroy(S.ev_fork);
 		if (S.ev_join) cudaEventDestroy(S.ev_join);
 		if (S.ev_done) cudaEventDestroy(S.ev_done);
@@ -514,6 +521,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	LaunchCtx L;
 	L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
 	L.nstreams = nstreams; L.num_sms = ctx->num_sms;
+	L.stream2 = S.s_heavy2; L.ev2_fork = S.ev_dft_fork; L.ev2_join = S.ev_dft_join;
 
 	if (!prof) {
 		CK(cudaEventRecord(S.ev_fork, sl));
@@ -772,6 +780,7 @@ extern "C" int stsgpu_debug_pattern_histogram(stsgpu_ctx *ctx, int64_t s, int bi
 	if (ctx->d_debug == NULL)
 		CK(cudaMalloc((void **) &ctx->d_debug, sizeof(uint32_t) << 21));
 	LaunchCtx L;
+	L.stream2 = nullptr; L.ev2_fork = L.ev2_join = nullptr;
 	L.stream = ctx->s_main; L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
 	L.nstreams = 1; L.num_sms = ctx->num_sms;
 	cudaError_t e = launch_debug_histogram(ctx->P, L, s, bits, ctx->d_debug);

@@ -23,7 +23,8 @@ struct Slot {
 	uint32_t *h_w = nullptr;
 	uint32_t *d_apen_hist = nullptr;
 	double2 *d_dft_work = nullptr;
-	cudaStream_t s_light = nullptr, s_heavy = nullptr;
+	cudaStream_t s_light = nullptr, s_heavy = nullptr, s_heavy2 = nullptr;
+	cudaEvent_t ev_dft_fork = nullptr, ev_dft_join = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_end = nullptr, ev_done = nullptr;
 	int nkernels = 0;
 	const char *k_name[STS_MAX_KERNELS] = { nullptr };

@@ -33,7 +33,10 @@
 #include "dft_math.cuh"
 
 #ifndef DFT_MINCTA
-#define DFT_MINCTA 3
+#define DFT_MINCTA 2
+#endif
+#ifndef DFT_NO_TW_POWERS
+#define DFT_TW_POWERS 1	/* fewer table lookups: r = 1, 2, 4, 8 loaded, the other twiddle powers by products */
 #endif
 #define QN1 256
 #define QN2 2048
@@ -75,6 +78,22 @@ __device__ __forceinline__ void bfly16(double2 *v)
 	}
 }
 
+/* x times W_16^r = exp(-2 pi i r / 16), r = 0..7 (compile-time r after unrolling) */
+__device__ __forceinline__ double2 cmul_w16(double2 x, int r)
+{
+	const double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, r2 = 0.70710678118654752440;
+	switch (r) {
+	case 0: return x;
+	case 1: return cmul(x, make_double2(c8, -s8));
+	case 2: return make_double2(r2 * (x.x + x.y), r2 * (x.y - x.x));
+	case 3: return cmul(x, make_double2(s8, -c8));
+	case 4: return cmi(x);
+	case 5: return cmul(x, make_double2(-s8, -c8));
+	case 6: return make_double2(r2 * (x.y - x.x), -r2 * (x.x + x.y));
+	default: return cmul(x, make_double2(-c8, -s8));
+	}
+}
+
 /* ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256, DFT_MINCTA)
 dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
@@ -101,9 +120,24 @@ dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__r
 
 	/* pass 1 (Ns = 16): k = t, outputs k1 = t + 16 r */
 	v[0] = buf[t * QCW + c];
+#ifdef DFT_TW_POWERS
+	{
+		double2 w[16];
+		w[1] = __ldg(D.q_twA + t); w[2] = __ldg(D.q_twA + 16 + t); w[4] = __ldg(D.q_twA + 3 * 16 + t);
+		w[8] = __ldg(D.q_twA + 7 * 16 + t);
+		w[3] = cmul(w[1], w[2]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+#pragma unroll
+		for (int r = 9; r < 16; r++)
+			w[r] = cmul(w[8], w[r - 8]);
+#pragma unroll
+		for (int r = 1; r < 16; r++)
+			v[r] = cmul(buf[(t + 16 * r) * QCW + c], w[r]);
+	}
+#else
 #pragma unroll
 	for (int r = 1; r < 16; r++)
 		v[r] = cmul(buf[(t + 16 * r) * QCW + c], __ldg(D.q_twA + (r - 1) * 16 + t));
+#endif
 	bfly16(v);
 	/* times W_N^(j2 k1) = W_N^(j2 t) (W_N^(16 j2))^r */
 	double2 tw = __ldg(D.q_e1 + t * QN2 + j2);
@@ -165,9 +199,24 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 		const int k = t & 15;
 		if (active) {
 			v[0] = row[pad16(t)];
+#ifdef DFT_TW_POWERS
+			{
+				double2 w[16];
+				w[1] = __ldg(D.q_twA + k); w[2] = __ldg(D.q_twA + 16 + k); w[4] = __ldg(D.q_twA + 3 * 16 + k);
+				w[8] = __ldg(D.q_twA + 7 * 16 + k);
+				w[3] = cmul(w[1], w[2]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+#pragma unroll
+				for (int r = 9; r < 16; r++)
+					w[r] = cmul(w[8], w[r - 8]);
+#pragma unroll
+				for (int r = 1; r < 16; r++)
+					v[r] = cmul(row[pad16(t + 128 * r)], w[r]);
+			}
+#else
 #pragma unroll
 			for (int r = 1; r < 16; r++)
 				v[r] = cmul(row[pad16(t + 128 * r)], __ldg(D.q_twA + (r - 1) * 16 + k));
+#endif
 			bfly16(v);
 		}
 		__syncthreads();
@@ -186,6 +235,22 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 	if (!self) {
 		const int ja = threadIdx.x, jb = 255 - threadIdx.x;
 		double2 za[8], zb[8];
+#ifdef DFT_TW_POWERS
+		{	/* twiddles W_2048^(j r): r = 1, 2, 4 from the table, the rest by products */
+			double2 wa[8], wb[8];
+			wa[1] = __ldg(D.q_twB + ja); wa[2] = __ldg(D.q_twB + 256 + ja); wa[4] = __ldg(D.q_twB + 3 * 256 + ja);
+			wb[1] = __ldg(D.q_twB + jb); wb[2] = __ldg(D.q_twB + 256 + jb); wb[4] = __ldg(D.q_twB + 3 * 256 + jb);
+			wa[3] = cmul(wa[1], wa[2]); wa[5] = cmul(wa[4], wa[1]); wa[6] = cmul(wa[4], wa[2]); wa[7] = cmul(wa[4], wa[3]);
+			wb[3] = cmul(wb[1], wb[2]); wb[5] = cmul(wb[4], wb[1]); wb[6] = cmul(wb[4], wb[2]); wb[7] = cmul(wb[4], wb[3]);
+			za[0] = buf[pad16(ja)];
+			zb[0] = buf[QROW + pad16(jb)];
+#pragma unroll
+			for (int r = 1; r < 8; r++) {
+				za[r] = cmul(buf[pad16(ja + 256 * r)], wa[r]);
+				zb[r] = cmul(buf[QROW + pad16(jb + 256 * r)], wb[r]);
+			}
+		}
+#else
 		za[0] = buf[pad16(ja)];
 		zb[0] = buf[QROW + pad16(jb)];
 #pragma unroll
@@ -193,14 +258,15 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 			za[r] = cmul(buf[pad16(ja + 256 * r)], __ldg(D.q_twB + (r - 1) * 256 + ja));
 			zb[r] = cmul(buf[QROW + pad16(jb + 256 * r)], __ldg(D.q_twB + (r - 1) * 256 + jb));
 		}
+#endif
 		bfly<8>(za);
 		bfly<8>(zb);
 		/* bin q = ra + 256 (ja + 256 r); its partner N - q = rb + 256 (jb + 256 (7 - r)) */
+		/* W_n^q = W_n^(ra + 256 ja) W_16^r: one table value, then the sixteenth roots of unity */
+		const double2 wq0 = cmul(w1, __ldg(D.q_p2 + ja));
 #pragma unroll
-		for (int r = 0; r < 8; r++) {
-			const double2 wq = cmul(w1, __ldg(D.q_p2 + ja + 256 * r));
-			cnt += post_pair(za[r], zb[7 - r], wq, D.T, T2, true);
-		}
+		for (int r = 0; r < 8; r++)
+			cnt += post_pair(za[r], zb[7 - r], cmul_w16(wq0, r), D.T, T2, true);
 	} else {
 		const int ja = threadIdx.x;
 		double2 za[8];
@@ -243,12 +309,33 @@ cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPla
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(dft_rows16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
 	if (e != cudaSuccess) return e;
-	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams) {
+	/*
+	 * Chunks of `work_streams` streams alternate between two streams with one work buffer each, so the
+	 * column pass of chunk i+1 runs beside the row pass of chunk i and the tail of one grid is filled
+	 * by the head of the next.
+	 */
+	const bool two = L.stream2 != nullptr && L.stream2 != L.stream && L.nstreams > work_streams;
+	if (two) {
+		e = cudaEventRecord(L.ev2_fork, L.stream);
+		if (e != cudaSuccess) return e;
+		e = cudaStreamWaitEvent(L.stream2, L.ev2_fork, 0);
+		if (e != cudaSuccess) return e;
+	}
+	int which = 0;
+	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams, which ^= 1) {
 		const int64_t cs = (L.nstreams - s0 < work_streams) ? L.nstreams - s0 : work_streams;
+		cudaStream_t st = (two && which) ? L.stream2 : L.stream;
+		double2 *wk = d_work + (size_t) which * work_streams * ((size_t) QN1 * QN2);
 		dim3 g1((unsigned) cs, QN2 / QCW);
-		dft_cols16<<<g1, 256, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		dft_cols16<<<g1, 256, smem1, st>>>(P, D, L.d_in, wk, s0);
 		dim3 g2((unsigned) cs, QN1 / 2 + 1);
-		dft_rows16<<<g2, 256, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		dft_rows16<<<g2, 256, smem2, st>>>(P, D, wk, L.d_st, s0);
+	}
+	if (two) {
+		e = cudaEventRecord(L.ev2_join, L.stream2);
+		if (e != cudaSuccess) return e;
+		e = cudaStreamWaitEvent(L.stream, L.ev2_join, 0);
+		if (e != cudaSuccess) return e;
 	}
 	return cudaGetLastError();
 }
