@@ -342,6 +342,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		}                                                                                                 \
 	} while (0)
 	ctx->nslots = p->pipeline_depth > 1 ? p->pipeline_depth : 1;
+	ctx->overlap_batches = !(getenv("STSGPU_SERIALIZE_BATCHES") && atoi(getenv("STSGPU_SERIALIZE_BATCHES")) > 0);
 	if (ctx->nslots > STS_MAX_SLOTS) ctx->nslots = STS_MAX_SLOTS;
 	int prio_lo = 0, prio_hi = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);		/* lo = least urgent, hi = most urgent */
@@ -366,6 +367,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_kdone, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreate(&S.ev_start), "cudaEventCreate");
 		CKC(cudaEventCreate(&S.ev_end), "cudaEventCreate");
 		for (int k = 0; k < STS_MAX_KERNELS; k++) {
@@ -481,6 +483,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		if (S.ev_fork) cudaEventDestroy(S.ev_fork);
 		if (S.ev_join) cudaEventDestroy(S.ev_join);
 		if (S.ev_done) cudaEventDestroy(S.ev_done);
+		if (S.ev_kdone) cudaEventDestroy(S.ev_kdone);
 		if (S.ev_start) cudaEventDestroy(S.ev_start);
 		if (S.ev_end) cudaEventDestroy(S.ev_end);
 		for (int k = 0; k < STS_MAX_KERNELS; k++) {
@@ -513,6 +516,15 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	const DevParams &P = ctx->P;
 	const stsgpu_layout &lay = ctx->lay;
 	cudaStream_t sl = S.s_light;
+	/*
+	 * By default the kernels of consecutive batches interleave freely (measured 1 % faster on B200).
+	 * STSGPU_SERIALIZE_BATCHES=1 keeps only the copy-ahead: this batch's upload (already queued on `sl`)
+	 * overlaps the previous batch's kernels, but its own kernels wait for them.
+	 */
+	if (ctx->nslots > 1 && ctx->submit_seq > 0 && !ctx->overlap_batches) {
+		Slot &prev = ctx->slots[(ctx->submit_seq - 1) % ctx->nslots];
+		CK(cudaStreamWaitEvent(sl, prev.ev_kdone, 0));
+	}
 	CK(cudaMemsetAsync(S.d_st, 0, (size_t) nstreams * lay.nst * sizeof(long long), sl));
 	CK(cudaEventRecord(S.ev_start, sl));
 	S.nkernels = 0;
@@ -585,6 +597,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		S.nkernels++;
 	}
 	CK(cudaEventRecord(S.ev_end, sl));
+	CK(cudaEventRecord(S.ev_kdone, sl));
 	CK(cudaMemcpyAsync(S.h_pv, S.d_pv, (size_t) nstreams * lay.npv * sizeof(double), cudaMemcpyDeviceToHost, sl));
 	CK(cudaMemcpyAsync(S.h_st, S.d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sl));
 	if (lay.nw)

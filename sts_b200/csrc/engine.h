@@ -25,7 +25,7 @@ struct Slot {
 	double2 *d_dft_work = nullptr;
 	cudaStream_t s_light = nullptr, s_heavy = nullptr, s_heavy2 = nullptr;
 	cudaEvent_t ev_dft_fork = nullptr, ev_dft_join = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_end = nullptr, ev_done = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_end = nullptr, ev_done = nullptr, ev_kdone = nullptr;
 	int nkernels = 0;
 	const char *k_name[STS_MAX_KERNELS] = { nullptr };
 	cudaEvent_t k_ev0[STS_MAX_KERNELS] = { nullptr }, k_ev1[STS_MAX_KERNELS] = { nullptr };
@@ -42,6 +42,7 @@ struct stsgpu_ctx {
 	int device = 0, num_sms = 0;
 
 	int nslots = 2;
+	bool overlap_batches = true;	/* false (STSGPU_SERIALIZE_BATCHES=1): kernels of consecutive batches do not interleave */
 	Slot slots[STS_MAX_SLOTS];
 	uint64_t submit_seq = 0;	/* the next submit / upload / generate uses slot submit_seq % nslots */
 	uint64_t wait_seq = 0;		/* the next wait completes slot wait_seq % nslots */
