@@ -356,6 +356,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(cudaMallocHost((void **) &S.h_pv, (size_t) B * lay.npv * sizeof(double)), "cudaMallocHost(pvals)");
 		CKC(cudaMallocHost((void **) &S.h_st, (size_t) B * (lay.nst + 1) * sizeof(long long)), "cudaMallocHost(istats)");
 		CKC(cudaMallocHost((void **) &S.h_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t)), "cudaMallocHost(wcount)");
+		CKC(cudaMalloc((void **) &S.d_hist_flags, (size_t) B * sizeof(uint32_t)), "cudaMalloc(hist flags)");
 		if (want_apen)
 			CKC(cudaMalloc((void **) &S.d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
 			    "cudaMalloc(apen histograms)");
@@ -474,7 +475,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		Slot &S = ctx->slots[i];
 		cudaFree(S.d_in); cudaFree(S.d_pv); cudaFree(S.d_st); cudaFree(S.d_w);
 		cudaFreeHost(S.h_pv); cudaFreeHost(S.h_st); cudaFreeHost(S.h_w);
-		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work);
+		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
 		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
 		if (S.s_heavy2) cudaStreamDestroy(S.s_heavy2);
@@ -561,7 +562,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		case G_BLOCKS: e = launch_blocks(P, L); launched = 3; break;
 		case G_RANK: e = launch_rank(P, L); launched = 1; break;
 		case G_NONOV: e = launch_nonoverlapping(P, L, ctx->d_templates); launched = 1; break;
-		case G_PATTERN: e = launch_pattern(P, L, S.d_apen_hist); launched = 1; break;
+		case G_PATTERN: e = launch_pattern(P, L, S.d_apen_hist, S.d_hist_flags); launched = 2; break;
 		case G_UNIVERSAL: e = launch_universal(P, L, ctx->d_log2tab); launched = 1; break;
 		case G_LC: e = launch_lc(P, L, ctx->d_class_lut); launched = 1; break;
 		case G_DFT:

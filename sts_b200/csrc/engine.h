@@ -22,6 +22,7 @@ struct Slot {
 	long long *h_st = nullptr;
 	uint32_t *h_w = nullptr;
 	uint32_t *d_apen_hist = nullptr;
+	uint32_t *d_hist_flags = nullptr;	/* streams the packed 16-bit histogram could not count exactly */
 	double2 *d_dft_work = nullptr;
 	cudaStream_t s_light = nullptr, s_heavy = nullptr, s_heavy2 = nullptr;
 	cudaEvent_t ev_dft_fork = nullptr, ev_dft_join = nullptr;

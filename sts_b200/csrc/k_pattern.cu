@@ -99,54 +99,13 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 
 /*
- * apen_hist layout per stream: [2^(apen_m+1) bins of level apen_m+1][2^apen_m bins of level apen_m]
+ * Statistics of every level from `Htop` bits down to the lowest one a test needs, from a histogram of
+ * 32-bit counters at `Htop` bits whose top `sb` bits equal `slice`; folds in place between levels.
  */
-__global__ void __launch_bounds__(HIST_THREADS)
-cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
-		   uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ debug_hist, int debug_bits)
+__device__ void emit_levels(const DevParams &P, uint32_t *hist, unsigned long long *red, int Htop, int sb, uint32_t slice,
+			    int64_t s, long long *__restrict__ st, uint32_t *__restrict__ apen_hist)
 {
-	extern __shared__ uint32_t hist[];
-	__shared__ unsigned long long red[HIST_THREADS / 32];
-	const int64_t s = blockIdx.x;
-	const uint32_t slice = blockIdx.y;
-	const int H = debug_hist ? debug_bits : P.hist_bits;
-	const int sb = debug_hist ? (H > 15 ? H - 15 : 0) : P.hist_slice_bits;
-	const int B = H - sb;					/* local histogram bits */
-	const uint32_t lmask = (1u << B) - 1u;
-	for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
-		hist[i] = 0;
-	__syncthreads();
-	const uint32_t *__restrict__ w = in + s * P.pitch_words;
-	const int64_t n = P.n;
-	const int64_t groups = (n + 31) >> 5;
-	for (int64_t g = threadIdx.x; g < groups; g += HIST_THREADS) {
-		const int64_t j0 = g * 32;
-		uint32_t cur, nxt;
-		if (j0 + 64 <= n) {
-			cur = ldw(w, g);
-			nxt = ldw(w, g + 1);
-		} else {
-			cur = cyc32(w, j0, n);
-			nxt = cyc32(w, j0 + 32, n);
-		}
-		int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
-#pragma unroll 8
-		for (int p = 0; p < 32; p++) {
-			if (p < cnt) {
-				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
-				if ((v >> B) == slice)
-					atomicAdd(&hist[v & lmask], 1u);
-			}
-		}
-	}
-	__syncthreads();
-	if (debug_hist) {
-		uint32_t *o = debug_hist + ((size_t) slice << B);
-		for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
-			o[i] = hist[i];
-		return;
-	}
-
+	const int H = Htop;
 	const int sm = (P.enabled & (1u << STSGPU_TEST_SERIAL)) ? P.serial_m : -100;
 	const int am = (P.enabled & (1u << STSGPU_TEST_APEN)) ? P.apen_m : -100;
 	int lowest = H;
@@ -202,7 +161,166 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 	}
 }
 
-cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist)
+/*
+ * apen_hist layout per stream: [2^(apen_m+1) bins of level apen_m+1][2^apen_m bins of level apen_m]
+ */
+__global__ void __launch_bounds__(HIST_THREADS)
+cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
+		   uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ debug_hist, int debug_bits,
+		   const uint32_t *__restrict__ only_flagged)
+{
+	extern __shared__ uint32_t hist[];
+	__shared__ unsigned long long red[HIST_THREADS / 32];
+	const int64_t s = blockIdx.x;
+	if (only_flagged && !only_flagged[s])
+		return;					/* the packed kernel already did this stream */
+	const uint32_t slice = blockIdx.y;
+	const int H = debug_hist ? debug_bits : P.hist_bits;
+	const int sb = debug_hist ? (H > 15 ? H - 15 : 0) : P.hist_slice_bits;
+	const int B = H - sb;					/* local histogram bits */
+	const uint32_t lmask = (1u << B) - 1u;
+	for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
+		hist[i] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t n = P.n;
+	const int64_t groups = (n + 31) >> 5;
+	for (int64_t g = threadIdx.x; g < groups; g += HIST_THREADS) {
+		const int64_t j0 = g * 32;
+		uint32_t cur, nxt;
+		if (j0 + 64 <= n) {
+			cur = ldw(w, g);
+			nxt = ldw(w, g + 1);
+		} else {
+			cur = cyc32(w, j0, n);
+			nxt = cyc32(w, j0 + 32, n);
+		}
+		int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
+#pragma unroll 8
+		for (int p = 0; p < 32; p++) {
+			if (p < cnt) {
+				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
+				if ((v >> B) == slice)
+					atomicAdd(&hist[v & lmask], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	if (debug_hist) {
+		uint32_t *o = debug_hist + ((size_t) slice << B);
+		for (int i = threadIdx.x; i < (1 << B); i += HIST_THREADS)
+			o[i] = hist[i];
+		return;
+	}
+
+	emit_levels(P, hist, red, H, sb, slice, s, st, apen_hist);
+}
+
+/*
+ * Fast path for H <= 16: the whole 2^H-bin histogram of one stream in ONE CTA with 16-bit counters,
+ * two bins per shared-memory word (bin 2x in the low half, 2x+1 in the high half), one atomic per
+ * window and no slice filter.  A counter can only overflow for wildly non-random input; every
+ * increment adds exactly one to the sum of all 16-bit fields unless a field wraps, which lowers it by
+ * 65535 or 65536, so "field sum == n" proves the counts exact.  Otherwise the stream is flagged and
+ * redone by the sliced 32-bit kernel above (never silently wrong).  Folding to H-1 bits is
+ * word = low + high, after which the counters are 32-bit and the common level code takes over.
+ */
+__global__ void __launch_bounds__(HIST_THREADS)
+cyclic_hist16_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
+		     uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ flags)
+{
+	extern __shared__ uint32_t hist[];
+	__shared__ unsigned long long red[HIST_THREADS / 32];
+	__shared__ int ok_s;
+	const int64_t s = blockIdx.x;
+	const int H = P.hist_bits;				/* 2 <= H <= 16 */
+	const int words = 1 << (H - 1);
+	for (int i = threadIdx.x; i < words; i += HIST_THREADS)
+		hist[i] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t n = P.n;
+	const int64_t groups = (n + 31) >> 5;
+	for (int64_t g = threadIdx.x; g < groups; g += HIST_THREADS) {
+		const int64_t j0 = g * 32;
+		uint32_t cur, nxt;
+		if (j0 + 64 <= n) {
+			cur = ldw(w, g);
+			nxt = ldw(w, g + 1);
+		} else {
+			cur = cyc32(w, j0, n);
+			nxt = cyc32(w, j0 + 32, n);
+		}
+		const int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
+#pragma unroll 8
+		for (int p = 0; p < 32; p++) {
+			if (p < cnt) {
+				const uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
+				atomicAdd(&hist[v >> 1], (v & 1u) ? 0x10000u : 1u);
+			}
+		}
+	}
+	__syncthreads();
+	{
+		unsigned long long tot = 0;
+		for (int i = threadIdx.x; i < words; i += HIST_THREADS)
+			tot += (hist[i] & 0xFFFFu) + (hist[i] >> 16);
+		tot = block_sum_u64(tot, red);
+		if (threadIdx.x == 0) {
+			ok_s = (tot == (unsigned long long) n) ? 1 : 0;
+			flags[s] = ok_s ? 0u : 1u;
+		}
+		__syncthreads();
+		if (!ok_s)
+			return;
+	}
+	const int sm = (P.enabled & (1u << STSGPU_TEST_SERIAL)) ? P.serial_m : -100;
+	const int am = (P.enabled & (1u << STSGPU_TEST_APEN)) ? P.apen_m : -100;
+	int lowest = H;
+	if (sm > 0) lowest = min(lowest, max(sm - 2, 1));
+	if (am > 0) lowest = min(lowest, am);
+	long long *o = st + s * P.nst;
+	{	/* level H from the packed fields */
+		const bool is_serial = (H == sm || H == sm - 1 || H == sm - 2);
+		const bool is_apen = (H == am + 1 || H == am);
+		if (is_serial || is_apen) {
+			unsigned long long sq = 0, lin = 0;
+			for (int i = threadIdx.x; i < words; i += HIST_THREADS) {
+				const unsigned long long c0 = hist[i] & 0xFFFFu, c1 = hist[i] >> 16;
+				sq += c0 * c0 + c1 * c1;
+				lin += (unsigned long long) (2 * i) * c0 + (unsigned long long) (2 * i + 1) * c1;
+			}
+			sq = block_sum_u64(sq, red);
+			if (is_apen)
+				lin = block_sum_u64(lin, red);
+			if (threadIdx.x == 0) {
+				if (is_serial)
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_SERIAL] + (sm - H)), sq);
+				if (is_apen) {
+					const int r = H - am;
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_APEN] + 2 + r), sq);
+					atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_APEN] + 4 + r), lin);
+				}
+			}
+			if (is_apen) {
+				uint32_t *dst = apen_hist + s * ((size_t) 3 << am) + (H == am + 1 ? 0 : ((size_t) 2 << am));
+				for (int i = threadIdx.x; i < words; i += HIST_THREADS) {
+					dst[2 * i] = hist[i] & 0xFFFFu;
+					dst[2 * i + 1] = hist[i] >> 16;
+				}
+			}
+		}
+	}
+	if (H == lowest)
+		return;
+	__syncthreads();
+	for (int i = threadIdx.x; i < words; i += HIST_THREADS)
+		hist[i] = (hist[i] & 0xFFFFu) + (hist[i] >> 16);
+	__syncthreads();
+	emit_levels(P, hist, red, H - 1, 0, 0u, s, st, apen_hist);
+}
+
+cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist, uint32_t *d_flags)
 {
 	if (!(P.enabled & ((1u << STSGPU_TEST_SERIAL) | (1u << STSGPU_TEST_APEN))))
 		return cudaSuccess;
@@ -211,8 +329,17 @@ cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_a
 	cudaError_t e = cudaFuncSetAttribute(cyclic_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	if (e != cudaSuccess)
 		return e;
+	const uint32_t *only_flagged = nullptr;
+	if (P.hist_bits >= 2 && P.hist_bits <= 16 && d_flags != nullptr) {
+		e = cudaFuncSetAttribute(cyclic_hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+		if (e != cudaSuccess)
+			return e;
+		cyclic_hist16_kernel<<<(unsigned) L.nstreams, HIST_THREADS, (size_t) sizeof(uint32_t) << (P.hist_bits - 1), L.stream>>>(
+			P, L.d_in, L.d_st, d_apen_hist, d_flags);
+		only_flagged = d_flags;
+	}
 	dim3 grid((unsigned) L.nstreams, 1u << P.hist_slice_bits);
-	cyclic_hist_kernel<<<grid, HIST_THREADS, smem, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, nullptr, 0);
+	cyclic_hist_kernel<<<grid, HIST_THREADS, smem, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, nullptr, 0, only_flagged);
 	return cudaGetLastError();
 }
 
@@ -227,6 +354,6 @@ cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64
 		return e;
 	dim3 grid(1, 1u << sb);
 	cyclic_hist_kernel<<<grid, HIST_THREADS, smem, L.stream>>>(P, L.d_in + stream_index * P.pitch_words, nullptr,
-								  nullptr, d_out, bits);
+								  nullptr, d_out, bits, nullptr);
 	return cudaGetLastError();
 }
