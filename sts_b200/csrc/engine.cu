@@ -362,7 +362,11 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			    "cudaMalloc(apen histograms)");
 		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
-		CKC(cudaStreamCreateWithPriority(&S.s_heavy2, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_uni, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_join_uni, cudaEventDisableTiming), "cudaEventCreate");
+		CKC(cudaEventCreateWithFlags(&S.ev_join_dft, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_dft_fork, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_dft_join, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming), "cudaEventCreate");
@@ -478,7 +482,11 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
 		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
-		if (S.s_heavy2) cudaStreamDestroy(S.s_heavy2);
+		if (S.s_uni) cudaStreamDestroy(S.s_uni);
+		if (S.s_dft[0]) cudaStreamDestroy(S.s_dft[0]);
+		if (S.s_dft[1]) cudaStreamDestroy(S.s_dft[1]);
+		if (S.ev_join_uni) cudaEventDestroy(S.ev_join_uni);
+		if (S.ev_join_dft) cudaEventDestroy(S.ev_join_dft);
 		if (S.ev_dft_fork) cudaEventDestroy(S.ev_dft_fork);
 		if (S.ev_dft_join) cudaEventDestroy(S.ev_dft_join);
 		if (S.ev_fork) cudaEventDestroy(S.ev_fork);
@@ -509,7 +517,7 @@ extern "C" int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out)
 /* ------------------------------------------------------------------------------------------ */
 struct Group {
 	const char *name;
-	bool heavy;		/* true: throughput-bound, low-priority stream */
+	int kind;		/* which of the slot's streams it runs on */
 };
 
 static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_iteration)
@@ -534,25 +542,29 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	LaunchCtx L;
 	L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
 	L.nstreams = nstreams; L.num_sms = ctx->num_sms;
-	L.stream2 = S.s_heavy2; L.ev2_fork = S.ev_dft_fork; L.ev2_join = S.ev_dft_join;
+	L.stream2 = S.s_dft[1]; L.ev2_fork = S.ev_dft_fork; L.ev2_join = S.ev_dft_join;
 
 	if (!prof) {
 		CK(cudaEventRecord(S.ev_fork, sl));
 		CK(cudaStreamWaitEvent(S.s_heavy, S.ev_fork, 0));
+		CK(cudaStreamWaitEvent(S.s_uni, S.ev_fork, 0));
+		CK(cudaStreamWaitEvent(S.s_dft[0], S.ev_fork, 0));
 	}
 	/*
-	 * Kernel groups.  Without profiling the throughput-bound groups run on the slot's low-priority
-	 * stream and the latency-bound ones on its high-priority stream, so that the small kernels get
-	 * SM slots as soon as they free up instead of queueing behind the big grids.
+	 * Kernel groups.  Without profiling each group goes to the stream of its kind (engine.h): the
+	 * small latency-bound kernels get SM slots as soon as they free up (high priority) instead of
+	 * queueing behind the big grids, and the ALU-bound, atomics-bound and FP64-bound grids co-run.
 	 */
 	enum { G_DFT, G_LC, G_PATTERN, G_UNIVERSAL, G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_COUNT };
+	enum { K_LIGHT, K_UNI, K_HEAVY, K_DFT };
 	static const Group groups[G_COUNT] = {
-		{ "dft", true }, { "linear_complexity", true }, { "pattern(serial,apen)", true },
-		{ "universal", false }, { "scan(freq,cusum,runs,excursions)", false },
-		{ "blocks(blockfreq,longestrun,overlapping)", false }, { "rank", false }, { "nonoverlapping", false },
+		{ "dft", K_DFT }, { "linear_complexity", K_HEAVY }, { "pattern(serial,apen)", K_HEAVY },
+		{ "universal", K_UNI }, { "scan(freq,cusum,runs,excursions)", K_LIGHT },
+		{ "blocks(blockfreq,longestrun,overlapping)", K_LIGHT }, { "rank", K_LIGHT }, { "nonoverlapping", K_LIGHT },
 	};
+	cudaStream_t kind_stream[4] = { sl, S.s_uni, S.s_heavy, S.s_dft[0] };
 	for (int g = 0; g < G_COUNT; g++) {
-		L.stream = (prof || !groups[g].heavy) ? sl : S.s_heavy;
+		L.stream = prof ? sl : kind_stream[groups[g].kind];
 		const int slot = S.nkernels;
 		CK(cudaEventRecord(S.k_ev0[slot], L.stream));
 		cudaError_t e = cudaSuccess;
@@ -582,6 +594,10 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	if (!prof) {
 		CK(cudaEventRecord(S.ev_join, S.s_heavy));
 		CK(cudaStreamWaitEvent(sl, S.ev_join, 0));
+		CK(cudaEventRecord(S.ev_join_uni, S.s_uni));
+		CK(cudaStreamWaitEvent(sl, S.ev_join_uni, 0));
+		CK(cudaEventRecord(S.ev_join_dft, S.s_dft[0]));
+		CK(cudaStreamWaitEvent(sl, S.ev_join_dft, 0));
 	}
 	L.stream = sl;
 	{

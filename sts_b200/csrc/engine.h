@@ -10,8 +10,11 @@
 /*
  * One batch in flight.  A context owns `nslots` of these and uses them round robin, so that the
  * host-to-device copy, the kernels and the record copy of consecutive batches overlap.  Each slot
- * has two streams: `s_light` (high priority: copies, the latency-bound kernels, the tails) and
- * `s_heavy` (low priority: pattern histograms, linear complexity, DFT), forked and joined by events.
+ * has five streams, forked and joined by events: `s_light` (high priority: copies, the small scan /
+ * block / rank / template kernels, the tails), `s_uni` (high priority: Universal, one long latency
+ * chain per stream), `s_heavy` (low priority: linear complexity = integer ALU, pattern histograms =
+ * shared-memory atomics) and `s_dft[2]` (low priority: the DFT's FP64 + LSU kernels, chunks
+ * alternating).  Work with different bottlenecks therefore shares the SMs.
  */
 struct Slot {
 	uint32_t *d_in = nullptr;
@@ -24,7 +27,8 @@ struct Slot {
 	uint32_t *d_apen_hist = nullptr;
 	uint32_t *d_hist_flags = nullptr;	/* streams the packed 16-bit histogram could not count exactly */
 	double2 *d_dft_work = nullptr;
-	cudaStream_t s_light = nullptr, s_heavy = nullptr, s_heavy2 = nullptr;
+	cudaStream_t s_light = nullptr, s_uni = nullptr, s_heavy = nullptr, s_dft[2] = { nullptr, nullptr };
+	cudaEvent_t ev_join_uni = nullptr, ev_join_dft = nullptr;
 	cudaEvent_t ev_dft_fork = nullptr, ev_dft_join = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_end = nullptr, ev_done = nullptr, ev_kdone = nullptr;
 	int nkernels = 0;
