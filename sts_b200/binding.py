@@ -18,7 +18,7 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
               "RandomExcursions", "RandomExcursionsVariant", "Serial", "LinearComplexity"]
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
-EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_submit",
+EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_dft_supported", "stsgpu_submit",
            "stsgpu_submit_resident", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_set_profiling",
@@ -73,6 +73,7 @@ def load_library():
     lib.stsgpu_destroy.argtypes = [vp]
     lib.stsgpu_destroy.restype = None
     lib.stsgpu_get_layout.argtypes = [vp, C.POINTER(Layout)]
+    lib.stsgpu_dft_supported.argtypes = [i64]
     lib.stsgpu_submit.argtypes = [vp, vp, i64, i64]
     lib.stsgpu_submit_resident.argtypes = [vp, i64, i64]
     lib.stsgpu_upload.argtypes = [vp, vp, i64]
@@ -103,6 +104,11 @@ def load_library():
     lib.stsgpu_abi_version.restype = i32
     _lib = lib
     return lib
+
+
+def dft_supported(n):
+    """can the engine's FFT take streams of n bits (n/2 = two 5-smooth factors <= 3200)"""
+    return bool(load_library().stsgpu_dft_supported(n))
 
 
 def default_params(**kw):

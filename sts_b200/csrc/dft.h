@@ -1,13 +1,20 @@
-/* dft.h - plan of the four-step FP64 FFT used by k_dft.cu (tables live in device memory) */
+/* dft.h - plan of the four-step FP64 FFT of the DFT test (tables live in device memory) */
 #pragma once
 #include <cuda_runtime.h>
 
+#define DFT_MAX_PASSES 16
+
 struct DftPlan {
-	int logN1, logN2;	/* N = n/2 = 2^logN1 * 2^logN2 */
+	/* N = n/2 complex points = N1 x N2; each 1-D FFT is a Stockham pass list with radices from {8, 5, 4, 3, 2} */
+	int N1, N2;
+	int np1, np2;
+	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
-	const double2 *wm;	/* exp(-2 pi i k / 1024), k < 1024: in-pass twiddles */
+	int fast;		/* n = 2^20: the specialised kernels of k_dft_fast.cu */
+	const double2 *w1;	/* exp(-2 pi i e / N1), e < N1 */
+	const double2 *w2;	/* exp(-2 pi i e / N2), e < N2 */
 	const double2 *tl;	/* exp(-2 pi i e / N), e < 1024 */
-	const double2 *th;	/* exp(-2 pi i 1024 e / N), e < max(1, N / 1024) */
+	const double2 *th;	/* exp(-2 pi i 1024 e / N), e < N / 1024 + 1 */
 	const double2 *p1;	/* exp(-2 pi i k1 / n), k1 < N1 */
 	const double2 *p2;	/* exp(-2 pi i N1 k2 / n), k2 < N2 */
 	/* tables of the n = 2^20 kernels (k_dft_fast.cu, N = 256 x 2048), NULL otherwise */
@@ -17,6 +24,8 @@ struct DftPlan {
 	const double2 *q_e2;	/* [2048]: exp(-2 pi i 16 j2 / N) */
 	const double2 *q_p1;	/* [256]:  exp(-2 pi i k1 / n) */
 	const double2 *q_p2;	/* [2048]: exp(-2 pi i 256 k2 / n) */
-	int dbg;		/* experiment switches (STSGPU_DFT_DBG), 0 in production */
 	double T;		/* sqrt(log(20) * n), discreteFourierTransform.c:142 */
 };
+
+/* host side (k_dft.cu): split N = n/2 into N1 x N2 and radix lists; false if n is not supported */
+bool dft_make_plan(long long n, DftPlan *D);

@@ -272,9 +272,10 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	int logn = 0;
 	while ((1LL << logn) < n) logn++;
 	if (en & (1u << STSGPU_TEST_DFT)) {
-		if ((1LL << logn) != n || logn < 10 || logn > 20)
+		if (!dft_make_plan(n, &ctx->dft))
 			return fail_create(ctx, STSGPU_E_UNSUPPORTED,
-					   "DFT test needs n = 2^k with 10 <= k <= 20 in this build; clear bit 7 of test_mask");
+					   "DFT test: n/2 must split into two 5-smooth factors <= 3200 (powers of two up to 2^23, "
+					   "10^6, 10^7 ...); clear bit 7 of test_mask for other stream lengths");
 	}
 
 	/* ---- tail constants (host libm, reference expressions) ---- */
@@ -414,30 +415,27 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(upload(&ctx->d_log2tab, tab.data(), tab.size()), "upload(log2 table)");
 	}
 	if (en & (1u << STSGPU_TEST_DFT)) {
-		DftPlan &D = ctx->dft;
-		const int logN = logn - 1;
-		D.logN2 = (logN + 1) / 2 > 10 ? 10 : (logN + 1) / 2;
-		D.logN1 = logN - D.logN2;
-		const int N1 = 1 << D.logN1, N2 = 1 << D.logN2;
+		DftPlan &D = ctx->dft;				/* N1, N2, radix lists: dft_make_plan above */
+		const int N1 = D.N1, N2 = D.N2;
 		const int64_t N = (int64_t) N1 * N2;
-		int cw = 512 / N1 > 8 ? 512 / N1 : 8;
-		if (cw > N2) cw = N2;
-		D.cw = cw;
-		D.dbg = getenv("STSGPU_DFT_DBG") ? atoi(getenv("STSGPU_DFT_DBG")) : 0;
+		D.fast = (n == (1LL << 20)) ? 1 : 0;
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
-		std::vector<double2> wm(1024), tl(1024), th((size_t) (N >= 1024 ? N / 1024 : 1)), p1(N1), p2(N2);
-		for (int k = 0; k < 1024; k++) { wm[k] = unit_root(k, 1024); tl[k] = unit_root(k, (long double) N); }
+		std::vector<double2> w1(N1), w2(N2), tl(1024), th((size_t) (N / 1024 + 1)), p1(N1), p2(N2);
+		for (int k = 0; k < N1; k++) w1[k] = unit_root(k, N1);
+		for (int k = 0; k < N2; k++) w2[k] = unit_root(k, N2);
+		for (int k = 0; k < 1024; k++) tl[k] = unit_root(k, (long double) N);
 		for (size_t k = 0; k < th.size(); k++) th[k] = unit_root((long double) k * 1024, (long double) N);
 		for (int k = 0; k < N1; k++) p1[k] = unit_root(k, (long double) n);
 		for (int k = 0; k < N2; k++) p2[k] = unit_root((long double) N1 * k, (long double) n);
 		double2 *d;
-		CKC(upload(&d, wm.data(), wm.size()), "upload(fft wm)"); D.wm = d; ctx->dft_tabs[0] = d;
+		CKC(upload(&d, w1.data(), w1.size()), "upload(fft w1)"); D.w1 = d; ctx->dft_tabs[0] = d;
+		CKC(upload(&d, w2.data(), w2.size()), "upload(fft w2)"); D.w2 = d; ctx->dft_tabs[11] = d;
 		CKC(upload(&d, tl.data(), tl.size()), "upload(fft tl)"); D.tl = d; ctx->dft_tabs[1] = d;
 		CKC(upload(&d, th.data(), th.size()), "upload(fft th)"); D.th = d; ctx->dft_tabs[2] = d;
 		CKC(upload(&d, p1.data(), p1.size()), "upload(fft p1)"); D.p1 = d; ctx->dft_tabs[3] = d;
 		CKC(upload(&d, p2.data(), p2.size()), "upload(fft p2)"); D.p2 = d; ctx->dft_tabs[4] = d;
 		D.q_twA = D.q_twB = D.q_e1 = D.q_e2 = D.q_p1 = D.q_p2 = nullptr;
-		if (D.logN1 == 9 && D.logN2 == 10) {				/* n = 2^20: k_dft_fast.cu */
+		if (D.fast) {							/* n = 2^20: k_dft_fast.cu (its own 256 x 2048 split) */
 			std::vector<double2> tA(15 * 16), tB(7 * 256), e1(16 * 2048), e2(2048), q1(256), q2(2048);
 			for (int r = 1; r < 16; r++)
 				for (int k = 0; k < 16; k++) tA[(r - 1) * 16 + k] = unit_root(k * r, 256);
@@ -459,6 +457,10 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		const char *envc = getenv("STSGPU_DFT_CHUNK");
 		if (envc && atoi(envc) > 0) chunk = atoi(envc);
 		if (chunk > B) chunk = B;
+		{	/* at most 1 GiB per work buffer (two per batch slot) */
+			const int64_t cap = ((int64_t) 1 << 30) / (N * (int64_t) sizeof(double2));
+			if (chunk > cap) chunk = cap > 0 ? cap : 1;
+		}
 		ctx->dft_chunk = chunk;
 		for (int i = 0; i < ctx->nslots; i++)
 			CKC(cudaMalloc((void **) &ctx->slots[i].d_dft_work, (size_t) 2 * chunk * N * sizeof(double2)), "cudaMalloc(fft work)");
@@ -501,9 +503,15 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		}
 	}
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
-	for (int i = 0; i < 11; i++) cudaFree(ctx->dft_tabs[i]);
+	for (int i = 0; i < 12; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
 	delete ctx;
+}
+
+extern "C" int stsgpu_dft_supported(int64_t n)
+{
+	DftPlan D;
+	return dft_make_plan(n, &D) ? 1 : 0;
 }
 
 extern "C" int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out)

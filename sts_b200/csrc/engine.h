@@ -64,7 +64,7 @@ struct stsgpu_ctx {
 	uint32_t *d_templates = nullptr;
 	uint8_t *d_class_lut = nullptr;
 	double *d_log2tab = nullptr;
-	double2 *dft_tabs[11] = { nullptr };
+	double2 *dft_tabs[12] = { nullptr };
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
 

@@ -1,245 +1,187 @@
 /*
- * k_dft.cu - discrete Fourier transform (spectral) test, discreteFourierTransform.c:326-411.
+ * k_dft.cu - discrete Fourier transform (spectral) test, discreteFourierTransform.c:326-411:
+ * the general path for every stream length whose half n/2 is 5-smooth (n = 10^7 = 2^7 5^7 of BASELINE
+ * config 4, n = 10^6, every power of two ...).  n = 2^20 takes the specialised kernels of
+ * k_dft_fast.cu instead.
  *
  * The reference hands X_i = +-1 (n reals) to libfftw3's r2c plan and counts the moduli below
  * T = sqrt(ln(20) n) among output bins 0 .. n/2 - 1.  Here the n reals are packed as N = n/2 complex
- * points z_j = x_2j + i x_2j+1, transformed by a hand-written FP64 four-step FFT (N = N1 x N2, both
- * <= 1024, so every 1-D FFT runs out of registers + shared memory), and un-packed with the usual
- * real-FFT post pass fused into the second kernel together with the |X| < T count:
+ * points z_j = x_2j + i x_2j+1 and transformed by a hand-written FP64 four-step FFT, N = N1 x N2 with
+ * j = N2 j1 + j2 and k = k1 + N1 k2:
  *
- *   dft_cols_kernel : for CW consecutive columns j2, FFT_N1 over j1 of z[N2 j1 + j2] (input decoded
- *                     straight from the packed bits), times W_N^(j2 k1), stored as Y[k1][j2]
- *                     (128-byte contiguous runs per k1).
+ *   dft_cols_kernel : for CW adjacent columns j2, FFT_N1 over j1 of z[N2 j1 + j2] (input decoded
+ *                     straight from the packed bits), times W_N^(j2 k1), stored as Y[k1][j2].
  *   dft_rows_kernel : for the row pair (k1, N1 - k1), FFT_N2 over j2 of Y[k1][.] gives
  *                     Z[k1 + N1 k2]; bins q and N - q live in the two rows of the pair, so
  *                     X_q = (Z_q + conj Z_{N-q})/2 - (i/2) W_n^q (Z_q - conj Z_{N-q}) and the count
  *                     are finished in shared memory; only N_1 leaves the kernel.
  *
- * Each 1-D FFT is a Stockham autosort FFT, radix 8 passes (plus one radix 4 or 2 pass), 8 complex
- * points per thread per pass, twiddles from L1-resident tables computed on the host.
+ * Each 1-D FFT is a Stockham autosort FFT out of two shared-memory buffers (ping-pong), one pass per
+ * radix of the plan (8, 5, 4, 3 or 2), a thread looping over the butterflies of the pass; twiddles
+ * come from a table of the N1-th (N2-th) roots of unity computed on the host in long double.
  *
  * Roofline: the intermediate Y is the traffic: 16 N bytes written + 16 N bytes read per stream
- * (8 MiB + 8 MiB at n = 2^20) against n/8 input bytes; FP64 work is about 5 N log2 N flop.
- * Only power-of-two n with 2^10 <= n <= 2^20 is handled by this path (N1 <= 512, N2 <= 1024).
+ * against n/8 input bytes; FP64 work is about 5 N log2 N flop.
  */
+#include <vector>
 #include "common.cuh"
 #include "dft.h"
-
 #include "dft_math.cuh"
 
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 
+#define GDFT_THREADS 256
+
+template <> __device__ __forceinline__ void bfly<3>(double2 *v)
+{
+	const double s = 0.86602540378443864676;
+	const double2 a = cadd(v[1], v[2]), b = csub(v[1], v[2]);
+	const double2 m = make_double2(v[0].x - 0.5 * a.x, v[0].y - 0.5 * a.y);
+	const double2 n = make_double2(s * b.y, -s * b.x);		/* -i s b */
+	v[0] = cadd(v[0], a);
+	v[1] = cadd(m, n);
+	v[2] = csub(m, n);
+}
+template <> __device__ __forceinline__ void bfly<5>(double2 *v)
+{
+	const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+	const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+	const double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+	const double2 m1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+	const double2 m2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+	const double2 n1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+	const double2 n2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+	v[0] = cadd(v[0], cadd(a1, a2));
+	v[1] = make_double2(m1.x + n1.y, m1.y - n1.x);		/* m1 - i n1 */
+	v[4] = make_double2(m1.x - n1.y, m1.y + n1.x);
+	v[2] = make_double2(m2.x + n2.y, m2.y - n2.x);
+	v[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
+}
+
+__device__ __forceinline__ void bfly_any(double2 *v, int R)
+{
+	switch (R) {
+	case 8: bfly<8>(v); break;
+	case 5: bfly<5>(v); break;
+	case 4: bfly<4>(v); break;
+	case 3: bfly<3>(v); break;
+	default: bfly<2>(v); break;
+	}
+}
+
+/*
+ * One Stockham pass of radix R over an FFT of length Nf laid out with element stride `es` (and a
+ * fixed offset already folded into src/dst): butterfly b reads src[(b + r Nf/R) es], multiplies by
+ * W_(Ns R)^(k r), k = b mod Ns, and writes dst[((b - k) R + k + r Ns) es].
+ */
+__device__ __forceinline__ void stockham_butterfly(const double2 *src, double2 *dst, int es, int Nf, int R, int Ns, int b,
+						     const double2 *__restrict__ wtab)
+{
+	double2 v[8];
+	const int q = Nf / R;
+#pragma unroll
+	for (int r = 0; r < 8; r++)
+		if (r < R)
+			v[r] = src[(b + r * q) * es];
+	const int k = b % Ns;
+	if (Ns > 1) {
+		const int step = Nf / (Ns * R);			/* W_(Ns R)^(k r) = W_Nf^(k r step) */
+#pragma unroll
+		for (int r = 1; r < 8; r++)
+			if (r < R)
+				v[r] = cmul(v[r], __ldg(wtab + (int64_t) k * r * step));
+	}
+	bfly_any(v, R);
+	const int base = (b - k) * R + k;
+#pragma unroll
+	for (int r = 0; r < 8; r++)
+		if (r < R)
+			dst[(base + r * Ns) * es] = v[r];
+}
+
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(GDFT_THREADS)
 dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
-	extern __shared__ double2 buf[];			/* [N1][CW] */
-	const int N1 = 1 << D.logN1, N2 = 1 << D.logN2, CW = D.cw;
+	extern __shared__ double2 buf[];			/* [2][N1][CW] */
+	const int N1 = D.N1, N2 = D.N2, CW = D.cw;
 	const int64_t sl = blockIdx.x;				/* stream inside the chunk */
 	const uint32_t *__restrict__ w = in + (stream0 + sl) * P.pitch_words;
 	double2 *__restrict__ Ys = Y + sl * ((int64_t) N1 * N2);
-	const int c = threadIdx.x % CW, t = threadIdx.x / CW;
-	const int j2 = blockIdx.y * CW + c;
-	const int n8 = D.logN1 / 3, rem = D.logN1 % 3;
-	const int nst = n8 + (rem ? 1 : 0);
+	const int j20 = blockIdx.y * CW;
+	double2 *a = buf, *b = buf + (size_t) N1 * CW;
 
-	auto load_bits = [&](int j1) -> double2 {
-		const int64_t p = 2 * ((int64_t) N2 * j1 + j2);
-		const uint32_t wd = ldw(w, p >> 5);
-		const uint32_t two = (wd >> (30 - (int) (p & 31))) & 3u;
-		return make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
-	};
-	auto load_smem = [&](int e) -> double2 { return buf[e * CW + c]; };
-	auto store_smem = [&](int e, double2 val) { buf[e * CW + c] = val; };
-	auto store_out = [&](int k1, double2 val) {
-		const int e = j2 * k1;				/* < N */
-		const double2 tw = cmul(__ldg(D.th + (e >> 10)), __ldg(D.tl + (e & 1023)));
-		Ys[(int64_t) k1 * N2 + j2] = cmul(val, tw);
-	};
-
+	/* z[N2 j1 + j2] = x_2j + i x_2j+1 from the packed bits */
+	for (int e = threadIdx.x; e < N1 * CW; e += GDFT_THREADS) {
+		const int j1 = e / CW, c = e % CW;
+		const int64_t p = 2 * ((int64_t) N2 * j1 + j20 + c);
+		const uint32_t two = (ldw(w, p >> 5) >> (30 - (int) (p & 31))) & 3u;
+		a[e] = make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
+	}
+	__syncthreads();
 	int Ns = 1;
-	for (int sidx = 0; sidx < nst; sidx++) {
-		const bool first = (sidx == 0), last = (sidx == nst - 1);
-		const int R = (sidx < n8) ? 8 : (1 << rem);
-		if (!first)
-			__syncthreads();			/* previous pass's stores are visible */
-		double2 v[8];
-		int dst[8];
-		if (R == 8) {
-			if (first) {
-#pragma unroll
-				for (int r = 0; r < 8; r++) v[r] = load_bits(t + r * (N1 >> 3));
-			} else {
-#pragma unroll
-				for (int r = 0; r < 8; r++) v[r] = load_smem(t + r * (N1 >> 3));
-			}
-			const int k = t & (Ns - 1);
-			if (Ns > 1) {
-				const int step = 1024 / (Ns * 8);
-#pragma unroll
-				for (int r = 1; r < 8; r++) v[r] = cmul(v[r], __ldg(D.wm + k * r * step));
-			}
-			bfly<8>(v);
-			const int base = (t - k) * 8 + k;
-#pragma unroll
-			for (int r = 0; r < 8; r++) dst[r] = base + r * Ns;
-		} else if (R == 4) {
-#pragma unroll
-			for (int u = 0; u < 2; u++) {
-				const int j = t + u * (N1 >> 3);
-#pragma unroll
-				for (int r = 0; r < 4; r++)
-					v[u * 4 + r] = first ? load_bits(j + r * (N1 >> 2)) : load_smem(j + r * (N1 >> 2));
-				const int k = j & (Ns - 1);
-				if (Ns > 1) {
-					const int step = 1024 / (Ns * 4);
-#pragma unroll
-					for (int r = 1; r < 4; r++) v[u * 4 + r] = cmul(v[u * 4 + r], __ldg(D.wm + k * r * step));
-				}
-				bfly<4>(&v[u * 4]);
-				const int base = (j - k) * 4 + k;
-#pragma unroll
-				for (int r = 0; r < 4; r++) dst[u * 4 + r] = base + r * Ns;
-			}
-		} else {
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const int j = t + u * (N1 >> 3);
-#pragma unroll
-				for (int r = 0; r < 2; r++)
-					v[u * 2 + r] = first ? load_bits(j + r * (N1 >> 1)) : load_smem(j + r * (N1 >> 1));
-				const int k = j & (Ns - 1);
-				if (Ns > 1)
-					v[u * 2 + 1] = cmul(v[u * 2 + 1], __ldg(D.wm + k * (1024 / (Ns * 2))));
-				bfly<2>(&v[u * 2]);
-				const int base = (j - k) * 2 + k;
-#pragma unroll
-				for (int r = 0; r < 2; r++) dst[u * 2 + r] = base + r * Ns;
-			}
+	for (int ps = 0; ps < D.np1; ps++) {
+		const int R = D.rad1[ps];
+		const int nb = N1 / R;
+		for (int e = threadIdx.x; e < nb * CW; e += GDFT_THREADS) {
+			const int bb = e / CW, c = e % CW;
+			stockham_butterfly(a + c, b + c, CW, N1, R, Ns, bb, D.w1);
 		}
-		if (!first)
-			__syncthreads();			/* everybody has read this pass's inputs */
-		if (last) {
-#pragma unroll
-			for (int r = 0; r < 8; r++) store_out(dst[r], v[r]);
-		} else {
-#pragma unroll
-			for (int r = 0; r < 8; r++) store_smem(dst[r], v[r]);
-		}
+		__syncthreads();
+		double2 *t = a; a = b; b = t;
 		Ns *= R;
+	}
+	/* times W_N^(j2 k1), out as Y[k1][j2] */
+	for (int e = threadIdx.x; e < N1 * CW; e += GDFT_THREADS) {
+		const int k1 = e / CW, c = e % CW;
+		const int64_t x = (int64_t) (j20 + c) * k1;		/* < N */
+		const double2 tw = cmul(__ldg(D.th + (x >> 10)), __ldg(D.tl + (x & 1023)));
+		Ys[(int64_t) k1 * N2 + j20 + c] = cmul(a[e], tw);
 	}
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GDFT_THREADS)
 dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
-	extern __shared__ double2 buf[];			/* [2][padi(N2)] */
+	extern __shared__ double2 buf[];			/* [2 rows][2][N2] */
 	__shared__ unsigned int cnt_s;
-	const int N1 = 1 << D.logN1, N2 = 1 << D.logN2;
+	const int N1 = D.N1, N2 = D.N2;
 	const int64_t sl = blockIdx.x;
 	const double2 *__restrict__ Ys = Y + sl * ((int64_t) N1 * N2);
-	const int pi = blockIdx.y;				/* pair index 0 .. N1/2 */
-	const int k1a = pi, k1b = (N1 - pi) & (N1 - 1);
+	const int k1a = blockIdx.y, k1b = (N1 - k1a) % N1;	/* row pair, k1a = 0 .. N1/2 */
 	const bool self = (k1a == k1b);
-	const int tpr = N2 >> 3;				/* threads per row */
-	const int rho = threadIdx.x / tpr, t = threadIdx.x % tpr;
-	const int rowlen = padi(N2) + 1;
-	const bool active = (rho == 0) || !self;
-	const int k1 = rho ? k1b : k1a;
-	const double2 *__restrict__ src = Ys + (int64_t) k1 * N2;
-	double2 *row = buf + rho * rowlen;
+	const int rows = self ? 1 : 2;
 	if (threadIdx.x == 0)
 		cnt_s = 0;
-
-	const int n8 = D.logN2 / 3, rem = D.logN2 % 3;
-	const int nst = n8 + (rem ? 1 : 0);
-	int Ns = 1;
-	for (int sidx = 0; sidx < nst; sidx++) {
-		const bool first = (sidx == 0);
-		const int R = (sidx < n8) ? 8 : (1 << rem);
-		double2 v[8];
-		int dst[8];
-		if (!first)
-			__syncthreads();
-		if (active) {
-			if (R == 8) {
-#pragma unroll
-				for (int r = 0; r < 8; r++) {
-					const int e = t + r * (N2 >> 3);
-					v[r] = first ? src[e] : row[padi(e)];
-				}
-				const int k = t & (Ns - 1);
-				if (Ns > 1) {
-					const int step = 1024 / (Ns * 8);
-#pragma unroll
-					for (int r = 1; r < 8; r++) v[r] = cmul(v[r], __ldg(D.wm + k * r * step));
-				}
-				bfly<8>(v);
-				const int base = (t - k) * 8 + k;
-#pragma unroll
-				for (int r = 0; r < 8; r++) dst[r] = base + r * Ns;
-			} else if (R == 4) {
-#pragma unroll
-				for (int u = 0; u < 2; u++) {
-					const int j = t + u * (N2 >> 3);
-#pragma unroll
-					for (int r = 0; r < 4; r++) {
-						const int e = j + r * (N2 >> 2);
-						v[u * 4 + r] = first ? src[e] : row[padi(e)];
-					}
-					const int k = j & (Ns - 1);
-					if (Ns > 1) {
-						const int step = 1024 / (Ns * 4);
-#pragma unroll
-						for (int r = 1; r < 4; r++)
-							v[u * 4 + r] = cmul(v[u * 4 + r], __ldg(D.wm + k * r * step));
-					}
-					bfly<4>(&v[u * 4]);
-					const int base = (j - k) * 4 + k;
-#pragma unroll
-					for (int r = 0; r < 4; r++) dst[u * 4 + r] = base + r * Ns;
-				}
-			} else {
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const int j = t + u * (N2 >> 3);
-#pragma unroll
-					for (int r = 0; r < 2; r++) {
-						const int e = j + r * (N2 >> 1);
-						v[u * 2 + r] = first ? src[e] : row[padi(e)];
-					}
-					const int k = j & (Ns - 1);
-					if (Ns > 1)
-						v[u * 2 + 1] = cmul(v[u * 2 + 1], __ldg(D.wm + k * (1024 / (Ns * 2))));
-					bfly<2>(&v[u * 2]);
-					const int base = (j - k) * 2 + k;
-#pragma unroll
-					for (int r = 0; r < 2; r++) dst[u * 2 + r] = base + r * Ns;
-				}
-			}
-		}
-		if (!first)
-			__syncthreads();
-		if (active) {
-#pragma unroll
-			for (int r = 0; r < 8; r++) row[padi(dst[r])] = v[r];
-		}
-		Ns *= R;
+	for (int e = threadIdx.x; e < rows * N2; e += GDFT_THREADS) {
+		const int r_ = e / N2, j2 = e % N2;
+		buf[(size_t) r_ * 2 * N2 + j2] = Ys[(int64_t) (r_ ? k1b : k1a) * N2 + j2];
 	}
 	__syncthreads();
-
+	int Ns = 1, cur = 0;
+	for (int ps = 0; ps < D.np2; ps++) {
+		const int R = D.rad2[ps];
+		const int nb = N2 / R;
+		for (int e = threadIdx.x; e < rows * nb; e += GDFT_THREADS) {
+			const int r_ = e / nb, bb = e % nb;
+			double2 *base = buf + (size_t) r_ * 2 * N2;
+			stockham_butterfly(base + cur * N2, base + (cur ^ 1) * N2, 1, N2, R, Ns, bb, D.w2);
+		}
+		__syncthreads();
+		cur ^= 1;
+		Ns *= R;
+	}
 	/* real-FFT post pass + count, discreteFourierTransform.c:392-411 (bins 0 .. n/2 - 1 = all q < N) */
 	unsigned int cnt = 0;
-	const int rows = self ? 1 : 2;
-	for (int e = threadIdx.x; e < rows * N2; e += blockDim.x) {
+	for (int e = threadIdx.x; e < rows * N2; e += GDFT_THREADS) {
 		const int r_ = e / N2, k2 = e % N2;
 		const int kq = r_ ? k1b : k1a;			/* q = kq + N1 k2 */
-		const double2 *mine = buf + r_ * rowlen;
-		const double2 *other = buf + (self ? 0 : (1 - r_)) * rowlen;
-		const int k2p = (kq == 0) ? ((N2 - k2) & (N2 - 1)) : (N2 - 1 - k2);
-		const double2 zq = mine[padi(k2)];
-		double2 zp = other[padi(k2p)];
+		const double2 *mine = buf + ((size_t) r_ * 2 + cur) * N2;
+		const double2 *other = buf + ((size_t) (self ? 0 : (1 - r_)) * 2 + cur) * N2;
+		const int k2p = (kq == 0) ? ((N2 - k2) % N2) : (N2 - 1 - k2);
+		const double2 zq = mine[k2];
+		double2 zp = other[k2p];
 		zp.y = -zp.y;					/* conj Z_{N-q} */
 		const double2 wq = cmul(__ldg(D.p1 + kq), __ldg(D.p2 + k2));	/* exp(-2 pi i q / n) */
 		const double2 sum = cadd(zq, zp), dif = csub(zq, zp);
@@ -258,17 +200,66 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 			  (unsigned long long) cnt_s);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* radix list of a 5-smooth length: 5s, 3s, then the power of two as 8s with a 4 4 / 4 / 2 remainder */
+static bool radix_list(int len, int *rad, int *np)
+{
+	int k = 0, two = 0;
+	while (len % 5 == 0) { rad[k++] = 5; len /= 5; if (k >= DFT_MAX_PASSES) return false; }
+	while (len % 3 == 0) { rad[k++] = 3; len /= 3; if (k >= DFT_MAX_PASSES) return false; }
+	while (len % 2 == 0) { two++; len /= 2; }
+	if (len != 1)
+		return false;
+	while (two >= 3 && two != 4) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 8; two -= 3; }
+	while (two >= 2) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 4; two -= 2; }
+	if (two == 1) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 2; }
+	*np = k;
+	return true;
+}
+
+bool dft_make_plan(long long n, DftPlan *D)
+{
+	if (n < 16 || (n & 1))
+		return false;
+	const long long N = n / 2;
+	const long long LIM = 3200;		/* rows: 2 rows x 2 buffers x N2 x 16 B <= 200 KiB */
+	long long best1 = 0, best2 = 0;
+	for (long long n2 = 2; n2 <= LIM && n2 <= N; n2++) {
+		if (N % n2)
+			continue;
+		const long long n1 = N / n2;
+		if (n1 > LIM || n1 < 2)
+			continue;
+		int r[DFT_MAX_PASSES], k;
+		if (!radix_list((int) n1, r, &k) || !radix_list((int) n2, r, &k))
+			continue;
+		/* the most balanced split (fewest passes over the longest FFT), N2 >= N1 */
+		if (n2 >= n1 && (best2 == 0 || n2 - n1 < best2 - best1)) {
+			best1 = n1;
+			best2 = n2;
+		}
+	}
+	if (best2 == 0)
+		return false;
+	D->N1 = (int) best1;
+	D->N2 = (int) best2;
+	radix_list(D->N1, D->rad1, &D->np1);
+	radix_list(D->N2, D->rad2, &D->np2);
+	int cw = 8;
+	while (cw > 1 && (D->N2 % cw != 0 || (size_t) 2 * D->N1 * cw * sizeof(double2) > 200 * 1024))
+		cw >>= 1;
+	D->cw = cw;
+	return true;
+}
+
 cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams)
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_DFT)))
 		return cudaSuccess;
-	const int N1 = 1 << D.logN1, N2 = 1 << D.logN2;
-	const int threads1 = D.cw * (N1 >> 3);
-	const size_t smem1 = (size_t) N1 * D.cw * sizeof(double2);
-	const int threads2 = 2 * (N2 >> 3);
-	const size_t smem2 = (size_t) 2 * (N2 + (N2 >> 3) + 1) * sizeof(double2);
-	if (D.logN1 == 9 && D.logN2 == 10)
+	if (D.fast)
 		return launch_dft_fast(P, L, D, d_work, work_streams);
+	const size_t smem1 = (size_t) 2 * D.N1 * D.cw * sizeof(double2);
+	const size_t smem2 = (size_t) 4 * D.N2 * sizeof(double2);
 	cudaError_t e;
 	e = cudaFuncSetAttribute(dft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
 	if (e != cudaSuccess) return e;
@@ -276,10 +267,10 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 	if (e != cudaSuccess) return e;
 	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams) {
 		const int64_t cs = (L.nstreams - s0 < work_streams) ? L.nstreams - s0 : work_streams;
-		dim3 g1((unsigned) cs, (unsigned) (N2 / D.cw));
-		dft_cols_kernel<<<g1, threads1, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
-		dim3 g2((unsigned) cs, (unsigned) (N1 / 2 + 1));
-		dft_rows_kernel<<<g2, threads2, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		dim3 g1((unsigned) cs, (unsigned) (D.N2 / D.cw));
+		dft_cols_kernel<<<g1, GDFT_THREADS, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		dim3 g2((unsigned) cs, (unsigned) (D.N1 / 2 + 1));
+		dft_rows_kernel<<<g2, GDFT_THREADS, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
 	}
 	return cudaGetLastError();
 }

@@ -32,8 +32,8 @@ def engine_for(sts, g, streams, mask=None):
     prm = golden_params(g)
     n = prm["n"]
     m = sts.ALL_TESTS if mask is None else mask
-    if n & (n - 1):
-        m &= ~(1 << 7)               # this build's FFT handles n = 2^k only (out of scope list)
+    if not sts.dft_supported(n):
+        m &= ~(1 << 7)               # n/2 not 5-smooth: the engine refuses the DFT loudly
     return sts.Engine(max_streams=streams, test_mask=m, **prm), m
 
 
@@ -233,7 +233,7 @@ def test_error_behaviour(sts):
     with pytest.raises(sts.EngineError):
         sts.Engine(max_streams=1, n=1001)                    # n % 8 != 0  (parse_args.c:939)
     with pytest.raises(sts.EngineError):
-        sts.Engine(max_streams=1, n=10 ** 7)                 # DFT at non power-of-two n: unsupported, said loudly
+        sts.Engine(max_streams=1, n=1000008)                 # DFT with n/2 not 5-smooth: unsupported, said loudly
     with sts.Engine(max_streams=2) as eng:
         with pytest.raises(sts.EngineError):
             eng.wait()                                       # wait without submit
@@ -246,12 +246,19 @@ def test_error_behaviour(sts):
         eng.wait()
 
 
-@pytest.mark.parametrize("n", [2048, 65536, 1 << 17, 400000])
+def test_dft_supported_lengths(sts):
+    for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
+        assert sts.dft_supported(n), n
+    for n in (1000008, 2 * 1000003, 14 * (1 << 16)):
+        assert not sts.dft_supported(n), n
+
+
+@pytest.mark.parametrize("n", [2048, 65536, 1 << 17, 400000, 6 * (1 << 17), 10 ** 6])
 def test_small_streams_against_oracle(sts, oracle, n):
     """short streams: most tests self-disable exactly like the X_init checks; the rest must still agree"""
     streams = 3
     raw = oracle.lcg_bytes(2, streams, n)
-    mask = sts.ALL_TESTS if n & (n - 1) == 0 else sts.ALL_TESTS & ~(1 << 7)
+    mask = sts.ALL_TESTS if sts.dft_supported(n) else sts.ALL_TESTS & ~(1 << 7)
     prm = dict(n=n, block_frequency_M=16384, non_overlapping_m=9, overlapping_m=9, apen_m=10, serial_m=16,
                linear_complexity_M=500)
     with sts.Engine(max_streams=streams, test_mask=mask, **prm) as eng:
