@@ -364,8 +364,9 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_uni, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
-		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
-		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		const int prio_dft = (getenv("STSGPU_DFT_PRIO_HI") && atoi(getenv("STSGPU_DFT_PRIO_HI"))) ? prio_hi : prio_lo;
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_dft), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_dft), "cudaStreamCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join_uni, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join_dft, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_dft_fork, cudaEventDisableTiming), "cudaEventCreate");

@@ -35,6 +35,11 @@
 #ifndef DFT_MINCTA
 #define DFT_MINCTA 2
 #endif
+#ifdef DFT_NO_BOUNDS
+#define DFT_BOUNDS
+#else
+#define DFT_BOUNDS __launch_bounds__(256, DFT_MINCTA)
+#endif
 #ifndef DFT_NO_TW_POWERS
 #define DFT_TW_POWERS 1	/* fewer table lookups: r = 1, 2, 4, 8 loaded, the other twiddle powers by products */
 #endif
@@ -95,7 +100,7 @@ __device__ __forceinline__ double2 cmul_w16(double2 x, int r)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256, DFT_MINCTA)
+__global__ void DFT_BOUNDS
 dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
 	extern __shared__ double2 buf[];			/* [256][16] */
@@ -167,7 +172,7 @@ __device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double
 	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
 }
 
-__global__ void __launch_bounds__(256, DFT_MINCTA)
+__global__ void DFT_BOUNDS
 dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
 	extern __shared__ double2 buf[];			/* [2][QROW] */

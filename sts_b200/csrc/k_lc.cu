@@ -19,7 +19,9 @@
  */
 #include "common.cuh"
 
+#ifndef LC_THREADS
 #define LC_THREADS 128
+#endif
 
 template <int W>
 __global__ void __launch_bounds__(LC_THREADS)
