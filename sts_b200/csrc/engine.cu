@@ -564,10 +564,10 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	 * small latency-bound kernels get SM slots as soon as they free up (high priority) instead of
 	 * queueing behind the big grids, and the ALU-bound, atomics-bound and FP64-bound grids co-run.
 	 */
-	enum { G_DFT, G_LC, G_PATTERN, G_UNIVERSAL, G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_COUNT };
+	enum { G_LC, G_DFT, G_PATTERN, G_UNIVERSAL, G_SCAN, G_BLOCKS, G_RANK, G_NONOV, G_COUNT };
 	enum { K_LIGHT, K_UNI, K_HEAVY, K_DFT };
 	static const Group groups[G_COUNT] = {
-		{ "dft", K_DFT }, { "linear_complexity", K_HEAVY }, { "pattern(serial,apen)", K_HEAVY },
+		{ "linear_complexity", K_HEAVY }, { "dft", K_DFT }, { "pattern(serial,apen)", K_HEAVY },
 		{ "universal", K_UNI }, { "scan(freq,cusum,runs,excursions)", K_LIGHT },
 		{ "blocks(blockfreq,longestrun,overlapping)", K_LIGHT }, { "rank", K_LIGHT }, { "nonoverlapping", K_LIGHT },
 	};

@@ -17,6 +17,7 @@
  *
  * Algorithmic bytes: n/8 per stream.  Integer work: M steps x ~4.5 word-ops x ceil((M+1)/32) words.
  */
+#include <stdlib.h>
 #include "common.cuh"
 
 #ifndef LC_THREADS
@@ -144,45 +145,55 @@ __device__ __forceinline__ void lc_phases(const uint32_t (&S)[W], uint32_t (&C)[
 	}
 }
 
+/*
+ * Grid-stride over the (stream, 128-block group) work items.  STSGPU_LC_BG=k launches only k CTAs per
+ * SM (a resident "background" grid): an experiment to make this integer-ALU kernel share the SMs with
+ * the FP64/LSU-bound DFT kernels.  It did not pay on B200 (the two still ran back to back, see
+ * DESIGN.md section 5), so the default is one CTA per work item.
+ */
 template <int W>
 __global__ void __launch_bounds__(LC_THREADS)
 lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
-	      long long *__restrict__ st)
+	      long long *__restrict__ st, int64_t nstreams, int groups_per_stream)
 {
 	__shared__ unsigned int cls[7];
-	const int64_t s = blockIdx.x;
-	if (threadIdx.x < 7)
-		cls[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t *__restrict__ w = in + s * P.pitch_words;
 	const int M = (int) P.lc_M;
-	/* whole warps stay alive (the window bound is a warp reduction); surplus lanes redo the last block */
-	const int64_t blk_raw = (int64_t) blockIdx.y * LC_THREADS + threadIdx.x;
-	const int64_t blk = min(blk_raw, P.lc_N - 1);
-	{
-		const int64_t start = blk * M;
-		uint32_t S[W], C[W], B[W];
+	for (int64_t item = blockIdx.x; item < nstreams * groups_per_stream; item += gridDim.x) {
+		const int64_t s = item / groups_per_stream;
+		const int by = (int) (item % groups_per_stream);
+		__syncthreads();				/* cls[] of the previous item has been flushed */
+		if (threadIdx.x < 7)
+			cls[threadIdx.x] = 0;
+		__syncthreads();
+		const uint32_t *__restrict__ w = in + s * P.pitch_words;
+		/* whole warps stay alive (the window bound is a warp reduction); surplus lanes redo the last block */
+		const int64_t blk_raw = (int64_t) by * LC_THREADS + threadIdx.x;
+		const int64_t blk = min(blk_raw, P.lc_N - 1);
+		{
+			const int64_t start = blk * M;
+			uint32_t S[W], C[W], B[W];
 #pragma unroll
-		for (int i = 0; i < W; i++) {
-			uint32_t v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * i - 1);
-			int valid = M + 1 - 32 * i;
-			if (valid < 32)
-				v &= mask_below((uint32_t) (valid > 0 ? valid : 0));
-			S[i] = v;
-			C[i] = 0;
-			B[i] = 0;
+			for (int i = 0; i < W; i++) {
+				uint32_t v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * i - 1);
+				int valid = M + 1 - 32 * i;
+				if (valid < 32)
+					v &= mask_below((uint32_t) (valid > 0 ? valid : 0));
+				S[i] = v;
+				C[i] = 0;
+				B[i] = 0;
+			}
+			C[0] = 0x40000000u;
+			B[0] = 0x80000000u;
+			int L = 0;
+			lc_phases<W, 0>(S, C, B, L, M);
+			if (blk_raw < P.lc_N)
+				atomicAdd(&cls[class_lut[L]], 1u);
 		}
-		C[0] = 0x40000000u;
-		B[0] = 0x80000000u;
-		int L = 0;
-		lc_phases<W, 0>(S, C, B, L, M);
-		if (blk_raw < P.lc_N)
-			atomicAdd(&cls[class_lut[L]], 1u);
+		__syncthreads();
+		if (threadIdx.x < 7 && cls[threadIdx.x])
+			atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
+				  (unsigned long long) cls[threadIdx.x]);
 	}
-	__syncthreads();
-	if (threadIdx.x < 7 && cls[threadIdx.x])
-		atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
-			  (unsigned long long) cls[threadIdx.x]);
 }
 
 /* any M up to 5000: the same recurrence with the arrays in (L1-resident) local memory */
@@ -250,13 +261,21 @@ cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_c
 		return cudaSuccess;
 	dim3 grid((unsigned) L.nstreams, (unsigned) ((P.lc_N + LC_THREADS - 1) / LC_THREADS));
 	const int W = (int) ((P.lc_M + 1 + 31) >> 5);
-	if (W <= 16)
-		lc_kernel_win<16><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
-	else if (W <= 24)
+	if (W <= 16) {
+		static int bg = -1;
+		if (bg < 0)
+			bg = getenv("STSGPU_LC_BG") ? atoi(getenv("STSGPU_LC_BG")) : 0;
+		const int64_t items = (int64_t) grid.x * grid.y;
+		int64_t ctas = bg > 0 ? (int64_t) bg * L.num_sms : items;
+		if (ctas > items) ctas = items;
+		lc_kernel_win<16><<<(unsigned) ctas, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st, L.nstreams, (int) grid.y);
+	}
+	else if (W <= 24) {
 		lc_kernel_reg<24><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
-	else if (W <= 32)
+	} else if (W <= 32) {
 		lc_kernel_reg<32><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
-	else
+	} else {
 		lc_kernel_generic<<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+	}
 	return cudaGetLastError();
 }
