@@ -3,17 +3,21 @@
  * CumulativeSums (cusum.c:221-236), Runs (runs.c:213-240), RandomExcursions
  * (randomExcursions.c:318-464) and RandomExcursionsVariant (randomExcursionsVariant.c:248-306).
  *
- * One CTA per bitstream.  Each of SCAN_WARPS warps owns a contiguous range of 1024-bit rows
- * (lane l holds word l of the row, so global loads are 128-byte coalesced).
- *   pass 1: popcount of the warp's range -> exclusive sum over warps gives the random walk value
- *           S at the start of every range;
- *   pass 2: per row, a warp shuffle scan gives S before every word; per word a byte LUT gives
- *           the max/min prefix (cusum), one XOR + popcount gives the run transitions, and only the
- *           words with |S| <= 41 (those that can touch the states -9..9 of the excursion tests)
- *           are walked bit by bit.
- * Excursion cycles are merged across words, rows and warps with an associative summary
- * (visits before the first zero, visits after the last zero), visit counts saturating at 5 in
- * 4-bit fields (only min(count, 5) is used, randomExcursions.c:441-451).
+ * One CTA per bitstream, the stream taken in chunks of 1024 rows of 1024 bits (lane l of a warp holds
+ * word l of a row, so global loads are 128-byte coalesced):
+ *   pass 1: popcount of every row -> block-wide exclusive scan = the random walk value S at the
+ *           start of every row (and the last bit of every row for the run count);
+ *   pass 2: rows are dealt to the warps ROUND ROBIN.  Per row a warp shuffle scan gives S before
+ *           every word; per word a byte LUT gives the max/min prefix (cusum), one XOR + popcount the
+ *           run transitions, and only the words with |S| <= 41 (those that can touch the states
+ *           -9..9 of the excursion tests) are walked bit by bit.  The walk returns to zero in
+ *           clusters, so contiguous row ranges per warp (the first version) left one warp with all
+ *           the bit-by-bit rows while seven waited at the barrier; dealt round robin they spread.
+ *   pass 3: excursion cycles cross word, row and chunk boundaries.  Every row leaves an associative
+ *           summary (zeros inside, visits before the first zero, visits after the last zero; cycles
+ *           strictly inside a row are recorded at once); the summaries are merged in row order by
+ *           256 threads -> 8 warps -> 1 thread.  Visit counts saturate at 5 in 4-bit fields (only
+ *           min(count, 5) is used, randomExcursions.c:441-451).
  *
  * Algorithmic bytes: n/8 per stream (the second pass re-reads the stream from L1/L2).
  */
@@ -21,6 +25,7 @@
 
 #define SCAN_WARPS 8
 #define SCAN_THREADS (SCAN_WARPS * 32)
+#define SCAN_ROWS 1024			/* rows per chunk */
 
 /* saturating (at 5) add of two words of eight 4-bit counters */
 __device__ __forceinline__ uint32_t nib_satadd5(uint32_t a, uint32_t b)
@@ -47,17 +52,43 @@ __device__ __forceinline__ void record_cycle(uint32_t c, unsigned int *v_s)
 	}
 }
 
+/*
+ * Excursion summary of a span of the walk: nz zeros inside; pre = visit counts before the first zero
+ * (of the whole span when nz == 0); suf = visit counts after the last zero (unused when nz == 0).
+ * append(b) merges the span that follows; the cycle closed at the seam is recorded.
+ */
+struct Exc {
+	uint32_t nz, pre, suf;
+	__device__ __forceinline__ void append(const Exc &b, unsigned int *v_s)
+	{
+		if (b.nz == 0) {
+			if (nz == 0)
+				pre = nib_satadd5(pre, b.pre);
+			else
+				suf = nib_satadd5(suf, b.pre);
+		} else {
+			if (nz == 0)
+				pre = nib_satadd5(pre, b.pre);
+			else
+				record_cycle(nib_satadd5(suf, b.pre), v_s);
+			suf = b.suf;
+			nz += b.nz;
+		}
+	}
+};
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st, int64_t nstreams)
 {
 	__shared__ uint32_t lut[256];
-	__shared__ int seg_ones[SCAN_WARPS];
-	__shared__ long long seg_bits[SCAN_WARPS];
-	__shared__ int seg_max[SCAN_WARPS], seg_min[SCAN_WARPS], seg_trans[SCAN_WARPS];
-	__shared__ int seg_nz[SCAN_WARPS];
-	__shared__ uint32_t seg_pre[SCAN_WARPS], seg_suf[SCAN_WARPS];
+	__shared__ int row_S[SCAN_ROWS];			/* ones per row, then walk value at the row start */
+	__shared__ uint8_t row_last[SCAN_ROWS];			/* last bit of the row */
+	__shared__ uint32_t row_nz[SCAN_ROWS], row_pre[SCAN_ROWS], row_suf[SCAN_ROWS];
+	__shared__ int warp_tot[SCAN_WARPS];
+	__shared__ Exc warp_exc[SCAN_WARPS];
 	__shared__ unsigned int v_s[6 * 8];
 	__shared__ unsigned int xi_s[18][SCAN_THREADS];
+	__shared__ int red_max[SCAN_WARPS], red_min[SCAN_WARPS], red_trans[SCAN_WARPS];
 
 	const int64_t s = blockIdx.x;
 	if (s >= nstreams)
@@ -84,170 +115,227 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 		xi_s[i][tid] = 0;
 
 	const int64_t nrows = (nwords + 31) >> 5;
-	const int64_t rpw = (nrows + SCAN_WARPS - 1) / SCAN_WARPS;
-	const int64_t r0 = min(nrows, warp * rpw), r1 = min(nrows, r0 + rpw);
+	int smax = 0, smin = 0, trans = 0;
+	long long total_ones = 0;
+	int S0 = 0;			/* walk value at the start of the chunk */
+	uint32_t last0 = 0;		/* last bit before the chunk */
+	Exc run;			/* thread 0: excursion state of everything before the chunk */
+	run.nz = run.pre = run.suf = 0;
 
-	/* ---- pass 1: ones in my range ---- */
-	int ones = 0;
-	for (int64_t r = r0; r < r1; r++) {
-		int64_t idx = r * 32 + lane;
-		if (idx < nwords)
-			ones += __popc(__ldg(w + idx));
-	}
-	ones = warp_sum(ones);
-	if (lane == 0) {
-		seg_ones[warp] = ones;
-		seg_bits[warp] = min(n, r1 * 1024) - min(n, r0 * 1024);
-	}
-	__syncthreads();
-	int S = 0;		/* walk value before my range */
-	int total_ones = 0;
-	for (int j = 0; j < SCAN_WARPS; j++) {
-		if (j < warp)
-			S += 2 * seg_ones[j] - (int) seg_bits[j];
-		total_ones += seg_ones[j];
-	}
-
-	/* ---- pass 2 ---- */
-	int smax = 0, smin = 0, trans = 0, nzeros = 0;
-	uint32_t open = 0;		/* visits of the currently open cycle (warp uniform) */
-	uint32_t first_pre = 0;		/* visits before the first zero of my range */
-	int range_has_zero = 0;
-	uint32_t carry = 0;		/* last bit of the previous word row */
-	if (r0 > 0 && r0 < nrows)
-		carry = ldw(w, r0 * 32 - 1) & 1u;
-
-	for (int64_t r = r0; r < r1; r++) {
-		const int64_t idx = r * 32 + lane;
-		const int64_t rem = n - idx * 32;
-		const int vb = rem >= 32 ? 32 : (rem > 0 ? (int) rem : 0);
-		const uint32_t wd = (idx < nwords) ? ldw(w, idx) : 0u;
-		const int d = 2 * __popc(wd) - vb;
-		const int incl = warp_scan_incl(d, lane);
-		const int Sb = S + incl - d;
-
-		/* cusum: max / min prefix inside the word */
-		if (vb == 32) {
-			int run = 0, mx = -64, mn = 64;
-#pragma unroll
-			for (int k = 3; k >= 0; k--) {
-				uint32_t e = lut[(wd >> (8 * k)) & 255u];
-				mx = max(mx, run + (int) ((e >> 8) & 255u) - 8);
-				mn = min(mn, run + (int) ((e >> 16) & 255u) - 8);
-				run += (int) (e & 255u) - 8;
-			}
-			smax = max(smax, Sb + mx);
-			smin = min(smin, Sb + mn);
-		} else if (vb > 0) {
-			int run = Sb;
-			for (int p = 0; p < vb; p++) {
-				run += ((wd >> (31 - p)) & 1u) ? 1 : -1;
-				smax = max(smax, run);
-				smin = min(smin, run);
+	for (int64_t c0 = 0; c0 < nrows; c0 += SCAN_ROWS) {
+		const int crow = (int) min((int64_t) SCAN_ROWS, nrows - c0);
+		__syncthreads();				/* previous chunk's shared arrays are consumed */
+		/* ---- pass 1: ones and last bit of every row ---- */
+		for (int r = warp; r < crow; r += SCAN_WARPS) {
+			const int64_t idx = (c0 + r) * 32 + lane;
+			const uint32_t wd = (idx < nwords) ? ldw(w, idx) : 0u;
+			const int ones = warp_sum(__popc(wd));
+			/* last valid bit of the row: stream bit min(n, 1024 (row + 1)) - 1 */
+			const int64_t lastbit = min(n, (c0 + r + 1) * 1024) - 1;
+			const uint32_t lw = __shfl_sync(0xffffffffu, wd, (int) ((lastbit >> 5) & 31));
+			if (lane == 0) {
+				row_S[r] = ones;
+				row_last[r] = (uint8_t) ((lw >> (31 - (int) (lastbit & 31))) & 1u);
 			}
 		}
+		for (int r = tid; r < SCAN_ROWS; r += SCAN_THREADS) {
+			row_nz[r] = 0;
+			row_pre[r] = 0;
+			row_suf[r] = 0;
+		}
+		__syncthreads();
+		/* ---- block scan: walk value at every row start (4 consecutive rows per thread) ---- */
+		{
+			int d[4], loc = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int r = 4 * tid + j;
+				int v = 0;
+				if (r < crow) {
+					const int64_t b0 = min(n, (c0 + r) * 1024), b1 = min(n, (c0 + r + 1) * 1024);
+					v = 2 * row_S[r] - (int) (b1 - b0);
+					total_ones += row_S[r];
+				}
+				d[j] = v;
+				loc += v;
+			}
+			const int incl = warp_scan_incl(loc, lane);
+			if (lane == 31)
+				warp_tot[warp] = incl;
+			__syncthreads();
+			int base = S0 + incl - loc;
+			for (int j = 0; j < warp; j++)
+				base += warp_tot[j];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int r = 4 * tid + j;
+				if (r < crow)
+					row_S[r] = base;
+				base += d[j];
+			}
+			int chunk_sum = 0;
+			for (int j = 0; j < SCAN_WARPS; j++)
+				chunk_sum += warp_tot[j];
+			__syncthreads();
+			S0 += chunk_sum;			/* every thread keeps the same running value */
+		}
 
-		/* runs: transitions between consecutive bits */
-		uint32_t prev = __shfl_up_sync(0xffffffffu, wd & 1u, 1);
-		if (lane == 0)
-			prev = carry;
-		uint32_t x = wd ^ ((wd >> 1) | (prev << 31));
-		uint32_t m = mask_below((uint32_t) vb);
-		if (idx == 0)
-			m &= 0x7FFFFFFFu;
-		trans += __popc(x & m);
-		carry = __shfl_sync(0xffffffffu, wd & 1u, 31);
+		/* ---- pass 2: rows round robin ---- */
+		for (int r = warp; r < crow; r += SCAN_WARPS) {
+			const int64_t idx = (c0 + r) * 32 + lane;
+			const int64_t rem = n - idx * 32;
+			const int vb = rem >= 32 ? 32 : (rem > 0 ? (int) rem : 0);
+			const uint32_t wd = (idx < nwords) ? ldw(w, idx) : 0u;
+			const int d = 2 * __popc(wd) - vb;
+			const int incl = warp_scan_incl(d, lane);
+			const int Sb = row_S[r] + incl - d;
 
-		/* excursions: only words that can reach |S| <= 9 */
-		if (want_exc) {
-			const bool hot = vb > 0 && abs(Sb) <= 41;
-			if (__any_sync(0xffffffffu, hot)) {
-				int nz = 0;
-				uint32_t pre = 0, cur = 0;
-				if (hot) {
-					int Sx = Sb;
-					for (int p = 0; p < vb; p++) {
-						Sx += ((wd >> (31 - p)) & 1u) ? 1 : -1;
-						if (Sx == 0) {
-							if (nz == 0)
-								pre = cur;
-							else
-								record_cycle(cur, v_s);
-							nz++;
-							cur = 0;
-						} else {
-							int a = abs(Sx);
-							if (a <= 9) {
-								xi_s[Sx < 0 ? Sx + 9 : Sx + 8][tid]++;
-								if (a <= 4) {
-									int sh = 4 * (Sx < 0 ? Sx + 4 : Sx + 3);
-									if (((cur >> sh) & 15u) < 5u)
-										cur += 1u << sh;
+			/* cusum: max / min prefix inside the word */
+			if (vb == 32) {
+				int run_ = 0, mx = -64, mn = 64;
+#pragma unroll
+				for (int k = 3; k >= 0; k--) {
+					uint32_t e = lut[(wd >> (8 * k)) & 255u];
+					mx = max(mx, run_ + (int) ((e >> 8) & 255u) - 8);
+					mn = min(mn, run_ + (int) ((e >> 16) & 255u) - 8);
+					run_ += (int) (e & 255u) - 8;
+				}
+				smax = max(smax, Sb + mx);
+				smin = min(smin, Sb + mn);
+			} else if (vb > 0) {
+				int run_ = Sb;
+				for (int p = 0; p < vb; p++) {
+					run_ += ((wd >> (31 - p)) & 1u) ? 1 : -1;
+					smax = max(smax, run_);
+					smin = min(smin, run_);
+				}
+			}
+
+			/* runs: transitions between consecutive bits */
+			uint32_t prev = __shfl_up_sync(0xffffffffu, wd & 1u, 1);
+			if (lane == 0)
+				prev = (r > 0) ? (uint32_t) row_last[r - 1] : last0;
+			uint32_t x = wd ^ ((wd >> 1) | (prev << 31));
+			uint32_t m = mask_below((uint32_t) vb);
+			if (idx == 0)
+				m &= 0x7FFFFFFFu;
+			trans += __popc(x & m);
+
+			/* excursions: only words that can reach |S| <= 9 */
+			if (want_exc) {
+				const bool hot = vb > 0 && abs(Sb) <= 41;
+				if (__any_sync(0xffffffffu, hot)) {
+					Exc e;
+					e.nz = e.pre = e.suf = 0;
+					if (hot) {
+						uint32_t cur = 0;
+						int Sx = Sb;
+						for (int p = 0; p < vb; p++) {
+							Sx += ((wd >> (31 - p)) & 1u) ? 1 : -1;
+							if (Sx == 0) {
+								if (e.nz == 0)
+									e.pre = cur;
+								else
+									record_cycle(cur, v_s);
+								e.nz++;
+								cur = 0;
+							} else {
+								int a = abs(Sx);
+								if (a <= 9) {
+									xi_s[Sx < 0 ? Sx + 9 : Sx + 8][tid]++;
+									if (a <= 4) {
+										int sh = 4 * (Sx < 0 ? Sx + 4 : Sx + 3);
+										if (((cur >> sh) & 15u) < 5u)
+											cur += 1u << sh;
+									}
 								}
 							}
 						}
+						if (e.nz == 0)
+							e.pre = cur;	/* no zero: "pre" carries the whole word */
+						else
+							e.suf = cur;
 					}
-					if (nz == 0)
-						pre = cur;	/* no zero: "pre" carries the whole word */
-				}
-				nzeros += nz;
-				/* ordered merge over the lanes (warp uniform) */
-				for (int l = 0; l < 32; l++) {
-					int nz_l = __shfl_sync(0xffffffffu, nz, l);
-					uint32_t pre_l = __shfl_sync(0xffffffffu, pre, l);
-					uint32_t suf_l = __shfl_sync(0xffffffffu, cur, l);
-					if (nz_l == 0) {
-						open = nib_satadd5(open, pre_l);
-					} else {
-						uint32_t closed = nib_satadd5(open, pre_l);
-						if (!range_has_zero) {
-							range_has_zero = 1;
-							first_pre = closed;
-						} else if (lane == 0) {
-							record_cycle(closed, v_s);
-						}
-						open = suf_l;
+					/* ordered tree merge over the lanes: lane l absorbs lane l + o */
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						Exc b;
+						b.nz = __shfl_down_sync(0xffffffffu, e.nz, o);
+						b.pre = __shfl_down_sync(0xffffffffu, e.pre, o);
+						b.suf = __shfl_down_sync(0xffffffffu, e.suf, o);
+						if ((lane & (2 * o - 1)) == 0)
+							e.append(b, v_s);
+					}
+					if (lane == 0) {
+						row_nz[r] = e.nz;
+						row_pre[r] = e.pre;
+						row_suf[r] = e.suf;
 					}
 				}
 			}
 		}
-		S += __shfl_sync(0xffffffffu, incl, 31);
+		last0 = (uint32_t) 0;				/* set after the barrier below (row_last of this chunk) */
+		__syncthreads();
+		last0 = row_last[crow - 1];
+
+		/* ---- pass 3: merge the row summaries in order: 4 rows per thread, 32 threads per warp, 8 warps ---- */
+		if (want_exc) {
+			Exc e;
+			e.nz = e.pre = e.suf = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int r = 4 * tid + j;
+				Exc b;
+				b.nz = row_nz[r];
+				b.pre = row_pre[r];
+				b.suf = row_suf[r];
+				e.append(b, v_s);
+			}
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				Exc b;
+				b.nz = __shfl_down_sync(0xffffffffu, e.nz, o);
+				b.pre = __shfl_down_sync(0xffffffffu, e.pre, o);
+				b.suf = __shfl_down_sync(0xffffffffu, e.suf, o);
+				if ((lane & (2 * o - 1)) == 0)
+					e.append(b, v_s);
+			}
+			if (lane == 0)
+				warp_exc[warp] = e;
+			__syncthreads();
+			if (tid == 0)
+				for (int j = 0; j < SCAN_WARPS; j++)
+					run.append(warp_exc[j], v_s);
+		}
 	}
 
 	smax = warp_max(smax);
 	smin = warp_min(smin);
 	trans = warp_sum(trans);
-	nzeros = warp_sum(nzeros);
+	total_ones = warp_sum_ll(total_ones);
 	if (lane == 0) {
-		seg_max[warp] = smax;
-		seg_min[warp] = smin;
-		seg_trans[warp] = trans;
-		seg_nz[warp] = range_has_zero ? nzeros : 0;
-		seg_pre[warp] = range_has_zero ? first_pre : open;
-		seg_suf[warp] = open;
+		red_max[warp] = smax;
+		red_min[warp] = smin;
+		red_trans[warp] = trans;
+		row_S[warp] = (int) total_ones;			/* <= 2^31 bits per stream */
 	}
 	__syncthreads();
 
-	/* ---- combine the ranges in order ---- */
 	if (tid == 0) {
 		int gmax = 0, gmin = 0, gtrans = 0;
-		long long J = 0;
-		uint32_t op = 0;
+		long long ones = 0;
 		for (int j = 0; j < SCAN_WARPS; j++) {
-			gmax = max(gmax, seg_max[j]);
-			gmin = min(gmin, seg_min[j]);
-			gtrans += seg_trans[j];
-			if (seg_nz[j] == 0) {
-				op = nib_satadd5(op, seg_pre[j]);
-			} else {
-				record_cycle(nib_satadd5(op, seg_pre[j]), v_s);
-				op = seg_suf[j];
-				J += seg_nz[j];
-			}
+			gmax = max(gmax, red_max[j]);
+			gmin = min(gmin, red_min[j]);
+			gtrans += red_trans[j];
+			ones += (unsigned int) row_S[j];
 		}
-		const long long Sfin = 2LL * total_ones - n;
+		long long J = run.nz;
+		const long long Sfin = 2LL * ones - n;
+		if (run.nz)		/* the first cycle: from the start of the stream to its first zero */
+			record_cycle(run.pre, v_s);
 		if (Sfin != 0) {	/* randomExcursions.c:345-347: the trailing partial cycle counts */
-			record_cycle(op, v_s);
+			record_cycle(run.nz ? run.suf : run.pre, v_s);
 			J++;
 		}
 		long long *o = st + s * P.nst;
@@ -263,7 +351,7 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 		}
 		if (P.enabled & (1u << STSGPU_TEST_RUNS)) {
 			long long *c = o + P.st_off[STSGPU_TEST_RUNS];
-			c[0] = total_ones;
+			c[0] = ones;
 			c[1] = 1 + gtrans;
 			/* c[2] (test_possible) is decided by the tail kernel in the reference's FP expression */
 		}
@@ -282,9 +370,9 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 		if (P.enabled & (1u << STSGPU_TEST_RND_EXCURSION_VAR))
 			o[P.st_off[STSGPU_TEST_RND_EXCURSION_VAR]] = J;
 	}
-	__syncthreads();	/* v_s atomics of thread 0 above are complete; xi_s is complete since the earlier barrier */
-	if ((P.enabled & (1u << STSGPU_TEST_RND_EXCURSION_VAR)) && warp < 18 / 3 + 0) {
-		/* 18 states, 3 per warp-iteration: warp j reduces states 3j..3j+2 */
+	__syncthreads();	/* xi_s is complete since the barriers above */
+	if ((P.enabled & (1u << STSGPU_TEST_RND_EXCURSION_VAR)) && warp < 6) {
+		/* 18 states, 3 per warp: warp j reduces states 3j..3j+2 */
 		for (int q = 0; q < 3; q++) {
 			int state = warp * 3 + q;
 			long long acc = 0;
