@@ -612,12 +612,25 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	{
 		const int slot = S.nkernels;
 		CK(cudaEventRecord(S.k_ev0[slot], sl));
-		cudaError_t e = launch_tails(P, ctx->K, L, S.d_apen_hist);
+		/* three independent kernels: p-value slots here, CumulativeSums and ApEn on two idle streams */
+		cudaStream_t s_cusum = prof ? sl : S.s_uni, s_apen = prof ? sl : S.s_heavy;
+		if (!prof) {
+			CK(cudaEventRecord(S.ev_fork, sl));
+			CK(cudaStreamWaitEvent(s_cusum, S.ev_fork, 0));
+			CK(cudaStreamWaitEvent(s_apen, S.ev_fork, 0));
+		}
+		cudaError_t e = launch_tails(P, ctx->K, L, S.d_apen_hist, s_cusum, s_apen);
 		if (e != cudaSuccess) {
 			set_err(ctx, "tails", e);
 			return STSGPU_E_CUDA;
 		}
-		ctx->launches += 1;
+		if (!prof) {
+			CK(cudaEventRecord(S.ev_join_uni, s_cusum));
+			CK(cudaStreamWaitEvent(sl, S.ev_join_uni, 0));
+			CK(cudaEventRecord(S.ev_join, s_apen));
+			CK(cudaStreamWaitEvent(sl, S.ev_join, 0));
+		}
+		ctx->launches += 3;
 		CK(cudaEventRecord(S.k_ev1[slot], sl));
 		S.k_name[slot] = "tails(p-values)";
 		S.nkernels++;

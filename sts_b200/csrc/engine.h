@@ -82,7 +82,8 @@ struct stsgpu_ctx {
 
 void stsgpu_comm_destroy_internal(stsgpu_ctx *ctx);
 
-cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist);
+cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
+			 cudaStream_t s_cusum, cudaStream_t s_apen);
 cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);
 cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits, uint32_t *d_out);

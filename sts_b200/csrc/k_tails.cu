@@ -403,18 +403,20 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
 	}
 }
 
-cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist)
+cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
+			 cudaStream_t s_cusum, cudaStream_t s_apen)
 {
+	/* the three kernels are independent chains: the caller forks s_cusum / s_apen off L.stream and joins them */
 	const int wpb = TAIL_THREADS / 32;
 	const int64_t groups = (L.nstreams + 31) >> 5;
 	const int64_t slot_warps = groups * P.npv;
 	tails_slots_kernel<<<(unsigned) ((slot_warps + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_w, L.d_pv,
 												      L.nstreams);
 	if (P.enabled & (1u << STSGPU_TEST_CUSUM))
-		tails_cusum_kernel<<<(unsigned) ((2 * L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_pv,
-														  L.nstreams);
+		tails_cusum_kernel<<<(unsigned) ((2 * L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, s_cusum>>>(P, K, L.d_st, L.d_pv,
+														 L.nstreams);
 	if (P.enabled & (1u << STSGPU_TEST_APEN))
-		tails_apen_kernel<<<(unsigned) ((L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, d_apen_hist,
-													     L.d_pv, L.nstreams);
+		tails_apen_kernel<<<(unsigned) ((L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, s_apen>>>(P, K, L.d_st, d_apen_hist,
+													   L.d_pv, L.nstreams);
 	return cudaGetLastError();
 }
