@@ -106,6 +106,25 @@ __device__ __forceinline__ int warp_scan_incl(int v, int lane)
 	return v;
 }
 
+/*
+ * An SM changes its L1 / shared-memory split only when it is idle, and the driver picks the split of a
+ * kernel from the shared memory its resident CTAs can use.  A kernel without shared memory therefore
+ * leaves the SM with (almost) none, and the DFT's 64-70 KiB CTAs cannot join it: measured here as the DFT
+ * making no progress at all while LinearComplexity ran in another stream.  LinearComplexity, the one
+ * long kernel without shared memory, therefore asks for dynamic shared memory it never touches
+ * (sts_pad_smem), which leaves the SM with a large split that the DFT CTAs can join; padding the
+ * other small kernels as well measured slower.  STSGPU_PAD_SMEM=0 switches it off.
+ */
+#include <stdlib.h>
+static inline size_t sts_pad_smem(size_t used, size_t target)
+{
+	static int on = -1;
+	if (on < 0)
+		on = getenv("STSGPU_PAD_SMEM") ? atoi(getenv("STSGPU_PAD_SMEM")) : 1;
+	return (on && used < target) ? target : used;
+}
+#define STS_PAD_KERNEL(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes))
+
 /* host-side launch bookkeeping shared by the kernel files */
 struct LaunchCtx {
 	cudaStream_t stream;

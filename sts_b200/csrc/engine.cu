@@ -572,7 +572,9 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		{ "blocks(blockfreq,longestrun,overlapping)", K_LIGHT }, { "rank", K_LIGHT }, { "nonoverlapping", K_LIGHT },
 	};
 	cudaStream_t kind_stream[4] = { sl, S.s_uni, S.s_heavy, S.s_dft[0] };
-	for (int g = 0; g < G_COUNT; g++) {
+	static const bool dft_first = getenv("STSGPU_DFT_FIRST") && atoi(getenv("STSGPU_DFT_FIRST")) > 0;
+	for (int gi = 0; gi < G_COUNT; gi++) {
+		const int g = (dft_first && gi < 2) ? 1 - gi : gi;	/* experiment: launch the DFT before LinearComplexity */
 		L.stream = prof ? sl : kind_stream[groups[g].kind];
 		const int slot = S.nkernels;
 		CK(cudaEventRecord(S.k_ev0[slot], L.stream));

@@ -146,13 +146,14 @@ __device__ __forceinline__ void lc_phases(const uint32_t (&S)[W], uint32_t (&C)[
 }
 
 /*
- * Grid-stride over the (stream, 128-block group) work items.  STSGPU_LC_BG=k launches only k CTAs per
- * SM (a resident "background" grid): an experiment to make this integer-ALU kernel share the SMs with
- * the FP64/LSU-bound DFT kernels.  It did not pay on B200 (the two still ran back to back, see
- * DESIGN.md section 5), so the default is one CTA per work item.
+ * Grid-stride over the (stream, 128-block group) work items, launched as a resident "background" grid
+ * of STSGPU_LC_BG (default 2) CTAs per SM: this kernel needs only the integer ALU pipe and 8K
+ * registers per CTA, the DFT needs the FP64 pipe, the LSU and shared memory, and with two small CTAs
+ * per SM (plus the padded shared-memory request, common.cuh) the two share every SM instead of taking
+ * turns.  Alone the kernel is ~15 % slower this way (8 warps per SM); the batch is ~5 % faster.
  */
 template <int W>
-__global__ void __launch_bounds__(LC_THREADS)
+__global__ void __launch_bounds__(LC_THREADS, 1024 / LC_THREADS)
 lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
 	      long long *__restrict__ st, int64_t nstreams, int groups_per_stream)
 {
@@ -264,11 +265,13 @@ cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_c
 	if (W <= 16) {
 		static int bg = -1;
 		if (bg < 0)
-			bg = getenv("STSGPU_LC_BG") ? atoi(getenv("STSGPU_LC_BG")) : 0;
+			bg = getenv("STSGPU_LC_BG") ? atoi(getenv("STSGPU_LC_BG")) : 2;
 		const int64_t items = (int64_t) grid.x * grid.y;
 		int64_t ctas = bg > 0 ? (int64_t) bg * L.num_sms : items;
 		if (ctas > items) ctas = items;
-		lc_kernel_win<16><<<(unsigned) ctas, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st, L.nstreams, (int) grid.y);
+		const size_t pad = sts_pad_smem(0, 24 * 1024);	/* a large L1/shared split: common.cuh */
+		STS_PAD_KERNEL(lc_kernel_win<16>, pad);
+		lc_kernel_win<16><<<(unsigned) ctas, LC_THREADS, pad, L.stream>>>(P, L.d_in, d_class_lut, L.d_st, L.nstreams, (int) grid.y);
 	}
 	else if (W <= 24) {
 		lc_kernel_reg<24><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
