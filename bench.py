@@ -323,8 +323,15 @@ def main():
     else:
         alg_bytes = B * (N_BITS // 8)
     achieved = alg_bytes / (kavg[top] * 1e-3) / 1e9
+    traffic = None
+    try:	# DRAM bytes of the same launches from the committed ncu capture (profiles/), scaled to B streams
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if top in tj["dram_bytes_per_group"] and tj["bits"] == N_BITS:
+            traffic = tj["dram_bytes_per_group"][top] * B / tj["streams"]
+    except Exception:
+        pass
     roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kavg[top], "algorithmic_bytes_per_launch_group": alg_bytes,
                 "all_kernel_groups_ms": {k: round(v, 4) for k, v in kavg.items()},
                 "in_region_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes_region.items()},

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn an `ncu --set full ... --page raw --csv` export of ONE batch (all kernels, serialised) into the
 per-kernel roofline table of profiles/: duration, algorithmic GB/s vs the measured HBM peak, DRAM
-traffic, and the pipe that bounds the kernel.  usage: profile_table.py raw.csv streams bits > table.md"""
+traffic, and the pipe that bounds the kernel.  usage: profile_table.py raw.csv streams bits [traffic.json] > table.md"""
 import csv
 import json
 import os
@@ -72,5 +72,11 @@ for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
     print("| %s | %d | %.1f | %.0f | %.3f | %.2f | %.0f | %.0f | %.0f | %.0f | %.0f | %d |" % (
         name, a["n"], us, gbs, gbs / peak, traf, a["alu"] / us, a["fp64"] / us, a["lsu"] / us, a["issue"] / us,
         a["occ"] / us, a["regs"]))
+if len(sys.argv) > 4:
+    groups = {"dft": ["dft_cols16", "dft_rows16"]}
+    out = {"streams": B, "bits": n, "source": os.path.basename(raw), "dram_bytes_per_group": {}}
+    for g, ks in groups.items():
+        out["dram_bytes_per_group"][g] = sum(agg[k]["rd"] + agg[k]["wr"] for k in ks if k in agg)
+    json.dump(out, open(sys.argv[4], "w"), indent=1)
 print("\nsum of kernel durations: %.1f us for %d streams of %d bits -> %.1f Gbit/s if run back to back" % (
     tot, B, n, B * n / (tot * 1e-6) / 1e9))
