@@ -59,3 +59,12 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("oracle_layout_for", "") or f == "__init__.py", \
                     "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_dft_supported_lengths():
+    """host-side FFT planning (no CUDA call): n/2 must split into two 5-smooth factors <= 3200"""
+    import sts_b200 as sts
+    for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
+        assert sts.dft_supported(n), n
+    for n in (1000008, 2 * 1000003, 14 * (1 << 16), 1 << 25):
+        assert not sts.dft_supported(n), n

@@ -246,13 +246,6 @@ def test_error_behaviour(sts):
         eng.wait()
 
 
-def test_dft_supported_lengths(sts):
-    for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
-        assert sts.dft_supported(n), n
-    for n in (1000008, 2 * 1000003, 14 * (1 << 16)):
-        assert not sts.dft_supported(n), n
-
-
 @pytest.mark.parametrize("n", [2048, 65536, 1 << 17, 400000, 6 * (1 << 17), 10 ** 6])
 def test_small_streams_against_oracle(sts, oracle, n):
     """short streams: most tests self-disable exactly like the X_init checks; the rest must still agree"""
