@@ -227,6 +227,38 @@ int stsgpu_comm_init(stsgpu_ctx *ctx, const uint8_t id[STSGPU_UNIQUE_ID_BYTES], 
 int stsgpu_gather_pvals(stsgpu_ctx *ctx, int root, const double **pvals_all);
 int stsgpu_comm_barrier(stsgpu_ctx *ctx);
 
+/* ---- assessment tallies on the device -------------------------------------------- */
+
+/*
+ * The uniformity / proportion assessment every X_metrics applies to a column of p-values
+ * (e.g. frequency.c:828-894 tally, :631-700 thresholds and uniformity; identical in all 15 tests) only
+ * needs, per p-value column, sampleCount, the count below alpha and the uniformity bin counts - all
+ * additive.  After stsgpu_assess_begin every batch adds its records to those tallies on the device as
+ * part of the batch, so a run of any length is assessed without keeping (or gathering) its p-values:
+ * the reference appends every p-value to state->p_val and stores a 64-byte struct per template p-value
+ * (defs.h:346-352), 79 GB at 2^23 streams.  Across GPUs the tallies are summed with one small
+ * collective (stsgpu_assess_reduce) instead of gathering 1.5 KB per stream.
+ */
+typedef struct stsgpu_metric {
+	int64_t sample_count;		/* p-values counted (excursion tests: only p > 0; NON_P_VALUE never) */
+	int64_t too_low;		/* of those, p < alpha */
+	int64_t pass_count;		/* sample_count - too_low (frequency.c:655-659) */
+	double proportion_min, proportion_max;	/* thresholds, frequency.c:664-666 */
+	double chi2, uniformity;	/* frequency.c:671-681: igamc((bins - 1) / 2, chi2 / 2) */
+	int32_t uniformity_passed, proportion_passed;	/* the verdicts of frequency.c:739-757 */
+} stsgpu_metric;
+
+/* start (or restart) tallying: uniformity_bins = tp.uniformity_bins (sqrt(iterations), or 10 with -O),
+ * alpha = tp.alpha (0.01), uniformity_level = tp.uniformity_level (0.0001); needs an idle engine */
+int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t uniformity_bins, double alpha, double uniformity_level);
+/* sum the tallies of all ranks of the communicator into every rank (NCCL all-reduce); no-op for one rank */
+int stsgpu_assess_reduce(stsgpu_ctx *ctx);
+/*
+ * Verdicts of everything tallied since stsgpu_assess_begin: metrics[npv] in record order, and, if freq
+ * is not NULL, the bin counts freq[npv][uniformity_bins].  Needs an idle engine (every batch waited for).
+ */
+int stsgpu_assess_finish(stsgpu_ctx *ctx, stsgpu_metric *metrics, int64_t *freq);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 
 /*

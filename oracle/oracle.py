@@ -50,6 +50,8 @@ def lib():
         _lib.oracle_pattern_histogram.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         _lib.oracle_lcg_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         _lib.oracle_lcg_bytes.restype = None
+        _lib.oracle_assess.argtypes = [C.POINTER(Layout), C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_igamc.argtypes = [C.c_double, C.c_double]
         _lib.oracle_igamc.restype = C.c_double
         _lib.oracle_igam.argtypes = [C.c_double, C.c_double]
@@ -95,6 +97,22 @@ def lcg_bytes(first_stream, nstreams, n=1 << 20):
     out = np.zeros(nstreams * n // 8, dtype=np.uint8)
     lib().oracle_lcg_bytes(first_stream, nstreams, n, out.ctypes.data)
     return out
+
+
+def assess(lay, pv, bins, alpha=0.01, uniformity_level=0.0001):
+    """uniformity / proportion assessment of pv[iterations, npv] -> dict of per-column arrays"""
+    pv = np.ascontiguousarray(pv, dtype=np.float64)
+    it, npv = pv.shape
+    tally = np.zeros((npv, 3), dtype=np.int64)
+    freq = np.zeros((npv, bins), dtype=np.int64)
+    fp = np.zeros((npv, 4), dtype=np.float64)
+    flags = np.zeros(npv, dtype=np.int32)
+    rc = lib().oracle_assess(C.byref(lay), pv.ctypes.data, it, bins, alpha, uniformity_level, tally.ctypes.data,
+                             freq.ctypes.data, fp.ctypes.data, flags.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle_assess failed: %d" % rc)
+    return dict(sample=tally[:, 0], toolow=tally[:, 1], passed=tally[:, 2], freq=freq, tmin=fp[:, 0], tmax=fp[:, 1],
+                chi2=fp[:, 2], uniformity=fp[:, 3], flags=flags)
 
 
 def igamc(a, x):

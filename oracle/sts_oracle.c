@@ -952,3 +952,67 @@ oracle_lcg_bytes(int64_t first_stream, int64_t nstreams, int64_t n, uint8_t *out
 		}
 	}
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Assessment of one run: frequency.c:828-894 (tally) and :631-700, :739-757 (thresholds, uniformity,
+ * verdict); the other 14 X_metrics are the same code with their own test number.
+ */
+int
+oracle_assess(const oracle_layout *lay, const double *pv, int64_t iterations, int64_t bins, double alpha,
+	      double uniformity_level, int64_t *tally, int64_t *freq, double *fp, int32_t *flags)
+{
+	if (lay == NULL || pv == NULL || bins < 1 || iterations < 0)
+		return -1;
+	for (int t = 1; t <= 15; t++) {
+		if (!((lay->enabled_mask >> t) & 1u))
+			continue;
+		const int is_excursion = (t == 12 || t == 13);		/* driver.c is_excursion[] */
+		for (int j = 0; j < lay->pv_cnt[t]; j++) {
+			const int q = lay->pv_off[t] + j;
+			long sampleCount = 0, toolow = 0;
+			int64_t *f = freq + (int64_t) q * bins;
+			memset(f, 0, (size_t) bins * sizeof(f[0]));
+			for (int64_t i = 0; i < iterations; i++) {
+				const double p_value = pv[i * lay->npv + q];
+				if (p_value == -99999999.0)			/* NON_P_VALUE, defs.h:314 */
+					continue;
+				if (is_excursion) {
+					if (p_value > 0.0)
+						++sampleCount;
+					else
+						continue;
+				} else {
+					++sampleCount;
+				}
+				if (p_value < alpha)
+					++toolow;
+				if (p_value >= 1.0)
+					++f[bins - 1];
+				else if (p_value >= 0.0)
+					++f[(int) floor(p_value * (double) bins)];
+				else
+					++f[0];
+			}
+			long passCount = ((sampleCount <= 0) || (sampleCount < toolow)) ? 0 : sampleCount - toolow;
+			const double p_hat = 1.0 - alpha;
+			const double tmax = (p_hat + 3.0 * sqrt((p_hat * alpha) / sampleCount)) * sampleCount;
+			const double tmin = (p_hat - 3.0 * sqrt((p_hat * alpha) / sampleCount)) * sampleCount;
+			double chi2 = 0.0, uniformity;
+			const double expCount = (double) sampleCount / bins;
+			if (expCount <= 0.0) {
+				uniformity = 0.0;
+			} else {
+				for (int64_t i = 0; i < bins; ++i)
+					chi2 += (f[i] - expCount) * (f[i] - expCount) / expCount;
+				uniformity = oracle_igamc((bins - 1.0) / 2.0, chi2 / 2.0);
+			}
+			const int uniformity_passed = !(expCount <= 0.0 || uniformity < uniformity_level);
+			const int proportion_passed = !(sampleCount == 0 || (passCount < tmin) || (passCount > tmax));
+			tally[3 * q] = sampleCount; tally[3 * q + 1] = toolow; tally[3 * q + 2] = passCount;
+			fp[4 * q] = tmin; fp[4 * q + 1] = tmax; fp[4 * q + 2] = chi2; fp[4 * q + 3] = uniformity;
+			flags[q] = uniformity_passed | (proportion_passed << 1);
+		}
+	}
+	return 0;
+}

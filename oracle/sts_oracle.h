@@ -51,6 +51,17 @@ int oracle_pattern_histogram(const uint8_t *raw, int64_t n, int bits, uint32_t *
 /* the LCG of tools/generators.c:797-905, byte-identical file contents */
 void oracle_lcg_bytes(int64_t first_stream, int64_t nstreams, int64_t n, uint8_t *out);
 
+/*
+ * The uniformity / proportion assessment every X_metrics applies to one column of p-values
+ * (e.g. frequency.c:828-894 tally, :631-700 thresholds and uniformity; the loop is identical in all
+ * 15 tests).  pv is iteration-major [iterations][npv]; columns of the excursion tests (12, 13) sample
+ * only p-values > 0.  Per column q: tally[q] = { sampleCount, toolow, passCount }, freq[q][bins],
+ * fp[q] = { proportion_threshold_min, proportion_threshold_max, chi2, uniformity },
+ * flags[q] = uniformity_passed | proportion_passed << 1  (the non-legacy branch of :739-757).
+ */
+int oracle_assess(const oracle_layout *lay, const double *pv, int64_t iterations, int64_t bins, double alpha,
+		  double uniformity_level, int64_t *tally, int64_t *freq, double *fp, int32_t *flags);
+
 /* p-value tails, exported for unit tests */
 double oracle_igamc(double a, double x);
 double oracle_igam(double a, double x);

@@ -21,7 +21,8 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
 EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_dft_supported", "stsgpu_submit",
            "stsgpu_submit_resident", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
-           "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_set_profiling",
+           "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
+           "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
            "stsgpu_kernel_count", "stsgpu_kernel_info", "stsgpu_last_batch_ms", "stsgpu_launch_count",
            "stsgpu_debug_pattern_histogram", "stsgpu_strerror", "stsgpu_last_error", "stsgpu_abi_version"]
 
@@ -35,6 +36,12 @@ class Params(C.Structure):
                 ("test_mask", C.c_uint32), ("pipeline_depth", C.c_int32), ("block_frequency_M", C.c_int64),
                 ("non_overlapping_m", C.c_int32), ("overlapping_m", C.c_int32), ("apen_m", C.c_int32),
                 ("serial_m", C.c_int32), ("linear_complexity_M", C.c_int64)]
+
+
+class Metric(C.Structure):
+    _fields_ = [("sample_count", C.c_int64), ("too_low", C.c_int64), ("pass_count", C.c_int64),
+                ("proportion_min", C.c_double), ("proportion_max", C.c_double), ("chi2", C.c_double),
+                ("uniformity", C.c_double), ("uniformity_passed", C.c_int32), ("proportion_passed", C.c_int32)]
 
 
 class Layout(C.Structure):
@@ -90,6 +97,9 @@ def load_library():
     lib.stsgpu_comm_init.argtypes = [vp, vp, i32, i32]
     lib.stsgpu_gather_pvals.argtypes = [vp, i32, C.POINTER(vp)]
     lib.stsgpu_comm_barrier.argtypes = [vp]
+    lib.stsgpu_assess_begin.argtypes = [vp, i64, C.c_double, C.c_double]
+    lib.stsgpu_assess_reduce.argtypes = [vp]
+    lib.stsgpu_assess_finish.argtypes = [vp, C.POINTER(Metric), vp]
     lib.stsgpu_set_profiling.argtypes = [vp, i32]
     lib.stsgpu_kernel_count.argtypes = [vp]
     lib.stsgpu_kernel_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
@@ -255,6 +265,26 @@ class Engine:
 
     def comm_barrier(self):
         self._ck(self.lib.stsgpu_comm_barrier(self.h), "comm_barrier")
+
+    # ---- assessment tallies on the device ----
+    def assess_begin(self, bins, alpha=0.01, uniformity_level=0.0001):
+        self._assess_bins = bins
+        self._ck(self.lib.stsgpu_assess_begin(self.h, bins, alpha, uniformity_level), "assess_begin")
+
+    def assess_reduce(self):
+        self._ck(self.lib.stsgpu_assess_reduce(self.h), "assess_reduce")
+
+    def assess_finish(self):
+        """-> dict of per-column arrays (same keys as oracle.assess)"""
+        npv, bins = self.layout.npv, self._assess_bins
+        m = (Metric * npv)()
+        freq = np.zeros((npv, bins), dtype=np.int64)
+        self._ck(self.lib.stsgpu_assess_finish(self.h, m, freq.ctypes.data), "assess_finish")
+        g = lambda f, dt: np.array([getattr(x, f) for x in m], dtype=dt)
+        return dict(sample=g("sample_count", np.int64), toolow=g("too_low", np.int64), passed=g("pass_count", np.int64),
+                    freq=freq, tmin=g("proportion_min", np.float64), tmax=g("proportion_max", np.float64),
+                    chi2=g("chi2", np.float64), uniformity=g("uniformity", np.float64),
+                    flags=g("uniformity_passed", np.int32) | (g("proportion_passed", np.int32) << 1))
 
     # ---- measurement ----
     def set_profiling(self, on):

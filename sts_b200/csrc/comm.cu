@@ -193,3 +193,24 @@ extern "C" int stsgpu_comm_barrier(stsgpu_ctx *ctx)
 		return STSGPU_E_CUDA;
 	return STSGPU_OK;
 }
+
+/* sum the assessment tallies of all ranks (include/stsgpu.h): the one collective of the assessment */
+extern "C" int stsgpu_assess_reduce(stsgpu_ctx *ctx)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->assessing || ctx->submit_seq != ctx->wait_seq) {
+		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_assess_reduce needs stsgpu_assess_begin and an idle engine");
+		return STSGPU_E_STATE;
+	}
+	if (ctx->nranks == 1)
+		return STSGPU_OK;
+	if (ctx->nccl_comm == NULL)
+		return STSGPU_E_STATE;
+	cudaSetDevice(ctx->device);
+	const size_t words = (size_t) ctx->lay.npv * (size_t) (ctx->assess_bins + 2);
+	NC(ctx, g_nccl.AllReduce(ctx->d_tally, ctx->d_tally, words, ncclUint64, ncclSum, (ncclComm_t) ctx->nccl_comm, ctx->s_main));
+	if (cudaStreamSynchronize(ctx->s_main) != cudaSuccess)
+		return STSGPU_E_CUDA;
+	return STSGPU_OK;
+}

@@ -504,6 +504,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		}
 	}
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
+	cudaFree(ctx->d_tally);
 	for (int i = 0; i < 12; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
 	delete ctx;
@@ -636,6 +637,14 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		CK(cudaEventRecord(S.k_ev1[slot], sl));
 		S.k_name[slot] = "tails(p-values)";
 		S.nkernels++;
+	}
+	if (ctx->assessing) {		/* add this batch's p-values to the assessment tallies */
+		cudaError_t e = launch_assess_tally(P, L, ctx->assess_bins, ctx->assess_alpha, ctx->d_tally);
+		if (e != cudaSuccess) {
+			set_err(ctx, "assess tally", e);
+			return STSGPU_E_CUDA;
+		}
+		ctx->launches += 1;
 	}
 	CK(cudaEventRecord(S.ev_end, sl));
 	CK(cudaEventRecord(S.ev_kdone, sl));
@@ -784,6 +793,66 @@ extern "C" void stsgpu_host_free(void *p)
 {
 	if (p)
 		cudaFreeHost(p);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t bins, double alpha, double level)
+{
+	if (ctx == NULL || bins < 1 || bins > (1 << 20))
+		return STSGPU_E_INVAL;
+	if (ctx->submit_seq != ctx->wait_seq) {
+		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_assess_begin needs an idle engine");
+		return STSGPU_E_STATE;
+	}
+	if (cudaSetDevice(ctx->device) != cudaSuccess)
+		return STSGPU_E_CUDA;
+	const size_t words = (size_t) ctx->lay.npv * (size_t) (bins + 2);
+	if (ctx->d_tally) cudaFree(ctx->d_tally);
+	ctx->d_tally = nullptr;
+	CK(cudaMalloc((void **) &ctx->d_tally, words * sizeof(unsigned long long)));
+	CK(cudaMemset(ctx->d_tally, 0, words * sizeof(unsigned long long)));
+	ctx->assess_bins = bins;
+	ctx->assess_alpha = alpha;
+	ctx->assess_level = level;
+	ctx->assessing = true;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_assess_finish(stsgpu_ctx *ctx, stsgpu_metric *metrics, int64_t *freq)
+{
+	if (ctx == NULL || metrics == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->assessing || ctx->submit_seq != ctx->wait_seq) {
+		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_assess_finish needs stsgpu_assess_begin and an idle engine");
+		return STSGPU_E_STATE;
+	}
+	if (cudaSetDevice(ctx->device) != cudaSuccess)
+		return STSGPU_E_CUDA;
+	const int npv = ctx->lay.npv;
+	const int64_t bins = ctx->assess_bins;
+	stsgpu_metric *d_out = nullptr;
+	CK(cudaMalloc((void **) &d_out, (size_t) npv * sizeof(stsgpu_metric)));
+	/* lgamma of the per-run constant (bins - 1) / 2 with glibc, like every other tail constant */
+	cudaError_t e = launch_assess_finish(ctx->P, bins, ctx->assess_alpha, ctx->assess_level, lgamma((bins - 1.0) / 2.0),
+					     ctx->d_tally, d_out, ctx->s_main);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(metrics, d_out, (size_t) npv * sizeof(stsgpu_metric), cudaMemcpyDeviceToHost, ctx->s_main);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(ctx->s_main);
+	cudaFree(d_out);
+	if (e != cudaSuccess) {
+		set_err(ctx, "assess finish", e);
+		return STSGPU_E_CUDA;
+	}
+	ctx->launches += 1;
+	if (freq) {
+		std::vector<unsigned long long> t((size_t) npv * (size_t) (bins + 2));
+		CK(cudaMemcpy(t.data(), ctx->d_tally, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		for (int q = 0; q < npv; q++)
+			for (int64_t b = 0; b < bins; b++)
+				freq[(int64_t) q * bins + b] = (int64_t) t[(size_t) q * (size_t) (bins + 2) + 2 + (size_t) b];
+	}
+	return STSGPU_OK;
 }
 
 /* ------------------------------------------------------------------------------------------ */

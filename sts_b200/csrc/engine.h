@@ -68,6 +68,12 @@ struct stsgpu_ctx {
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
 
+	/* assessment tallies (stsgpu_assess_*): per column [sample, toolow, freq[bins]] */
+	bool assessing = false;
+	int64_t assess_bins = 0;
+	double assess_alpha = 0.01, assess_level = 0.0001;
+	unsigned long long *d_tally = nullptr;
+
 	bool profiling = false;
 	int64_t launches = 0;
 
@@ -85,5 +91,8 @@ void stsgpu_comm_destroy_internal(stsgpu_ctx *ctx);
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
 			 cudaStream_t s_cusum, cudaStream_t s_apen);
 cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
+cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally);
+cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha, double level, double lgam, const unsigned long long *d_tally,
+				 stsgpu_metric *d_out, cudaStream_t stream);
 cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);
 cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits, uint32_t *d_out);

@@ -403,6 +403,97 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
 	}
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Assessment tallies (include/stsgpu.h, stsgpu_assess_*): frequency.c:828-894, one thread per
+ * (stream, p-value column) of the batch; per column [sampleCount, toolow, freq[bins]].
+ */
+__global__ void __launch_bounds__(256)
+assess_tally_kernel(DevParams P, const double *__restrict__ pv_all, int64_t nstreams, int64_t bins, double alpha,
+		    unsigned long long *__restrict__ tally)
+{
+	const int64_t idx = (int64_t) blockIdx.x * 256 + threadIdx.x;
+	if (idx >= nstreams * P.npv)
+		return;
+	const int q = (int) (idx % P.npv);
+	const double p_value = pv_all[idx];
+	if (p_value == NONP)
+		return;					/* the test was not possible for this iteration */
+	const int e12 = P.pv_off[STSGPU_TEST_RND_EXCURSION], e13 = P.pv_off[STSGPU_TEST_RND_EXCURSION_VAR];
+	const bool is_excursion = ((P.enabled & (1u << STSGPU_TEST_RND_EXCURSION)) && q >= e12 && q < e12 + 8) ||
+				  ((P.enabled & (1u << STSGPU_TEST_RND_EXCURSION_VAR)) && q >= e13 && q < e13 + 18);
+	if (is_excursion && !(p_value > 0.0))
+		return;					/* excursion tests only sample p-values > 0 */
+	unsigned long long *t = tally + (int64_t) q * (bins + 2);
+	atomicAdd(&t[0], 1ull);
+	if (p_value < alpha)
+		atomicAdd(&t[1], 1ull);
+	int64_t b;
+	if (p_value >= 1.0)
+		b = bins - 1;
+	else if (p_value >= 0.0)
+		b = (int) floor(p_value * (double) bins);
+	else
+		b = 0;
+	atomicAdd(&t[2 + b], 1ull);
+}
+
+/* frequency.c:631-700 and :739-757, one thread per column */
+__global__ void __launch_bounds__(128)
+assess_finish_kernel(DevParams P, int64_t bins, double alpha, double level, double lgam,
+		     const unsigned long long *__restrict__ tally, stsgpu_metric *__restrict__ out)
+{
+	const int q = blockIdx.x * 128 + threadIdx.x;
+	if (q >= P.npv)
+		return;
+	const unsigned long long *t = tally + (int64_t) q * (bins + 2);
+	const long long sampleCount = (long long) t[0], toolow = (long long) t[1];
+	long long passCount;
+	if ((sampleCount <= 0) || (sampleCount < toolow))
+		passCount = 0;
+	else
+		passCount = sampleCount - toolow;
+	const double p_hat = 1.0 - alpha;
+	const double tmax = (p_hat + 3.0 * sqrt((p_hat * alpha) / sampleCount)) * sampleCount;
+	const double tmin = (p_hat - 3.0 * sqrt((p_hat * alpha) / sampleCount)) * sampleCount;
+	double chi2 = 0.0, uniformity;
+	const double expCount = (double) sampleCount / bins;
+	if (expCount <= 0.0) {
+		uniformity = 0.0;
+	} else {
+		for (int64_t i = 0; i < bins; ++i) {
+			const double f = (double) (long long) t[2 + i];
+			chi2 += (f - expCount) * (f - expCount) / expCount;
+		}
+		uniformity = d_igamc((bins - 1.0) / 2.0, chi2 / 2.0, lgam);
+	}
+	stsgpu_metric m;
+	m.sample_count = sampleCount;
+	m.too_low = toolow;
+	m.pass_count = passCount;
+	m.proportion_min = tmin;
+	m.proportion_max = tmax;
+	m.chi2 = chi2;
+	m.uniformity = uniformity;
+	m.uniformity_passed = !(expCount <= 0.0 || uniformity < level);
+	m.proportion_passed = !(sampleCount == 0 || (passCount < tmin) || (passCount > tmax));
+	out[q] = m;
+}
+
+cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally)
+{
+	const int64_t total = L.nstreams * P.npv;
+	assess_tally_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, L.stream>>>(P, L.d_pv, L.nstreams, bins, alpha, d_tally);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha, double level, double lgam,
+				 const unsigned long long *d_tally, stsgpu_metric *d_out, cudaStream_t stream)
+{
+	assess_finish_kernel<<<(unsigned) ((P.npv + 127) / 128), 128, 0, stream>>>(P, bins, alpha, level, lgam, d_tally, d_out);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
 			 cudaStream_t s_cusum, cudaStream_t s_apen)
 {

@@ -9,7 +9,8 @@ GOLDEN_DIR = os.path.join(HERE, "golden")
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [x for x in names if not x.startswith("assess_")]	# assess_*: assessment reports, see make_assess_golden.py
 
 
 def load_golden(name):

@@ -211,6 +211,49 @@ def test_pipelined_batches_complete_in_order(sts, oracle):
         assert (pv == rpv).all() and (st == rst).all() and (w == rw).all()
 
 
+def test_assessment_tallies_match_reference_report(sts, oracle):
+    """stsgpu_assess_*: per-column uniformity bins, proportion and uniformity p-value of 64 LCG streams, tallied
+    on the device batch by batch (two batches in flight), against the reference's own finalAnalysisReport.txt
+    (sts -O: 10 bins; tests/golden/make_assess_golden.py) and against the oracle's restatement of X_metrics."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "assess_lcg_64.npz"))
+    streams, B, n = int(g["streams"]), 16, 1 << 20
+    raw = oracle.lcg_bytes(0, streams)
+    pvs = []
+    with sts.Engine(max_streams=B, pipeline_depth=2) as eng:
+        eng.assess_begin(10)
+        pending = 0
+        for b in range(streams // B):
+            eng.submit(raw[b * B * n // 8:(b + 1) * B * n // 8].copy(), B, b * B)
+            pending += 1
+            if pending == 2:
+                eng.wait()
+                pvs.append(eng.results()[0])
+                pending -= 1
+        while pending:
+            eng.wait()
+            pvs.append(eng.results()[0])
+            pending -= 1
+        a = eng.assess_finish()
+        lay = eng.layout
+        # a different bin count restarts the tallies: sqrt(iterations) bins, parse_args.c:791-793
+        eng.assess_begin(8, 0.01, 0.0001)
+        eng.run(raw[:B * n // 8].copy(), B, 0)
+        a8 = eng.assess_finish()
+    pv = np.concatenate(pvs)
+    assert (a["freq"] == g["bins"]).all() and (a["sample"] == g["sample"]).all() and (a["passed"] == g["passed"]).all()
+    assert np.abs(a["uniformity"] - g["uniformity"]).max() <= 5.01e-7          # the report prints %8.6f
+    assert ((a["flags"] & 1) == 0).sum() == g["uniformity_failed"].sum()
+    assert ((a["flags"] & 2) == 0).sum() == g["proportion_failed"].sum()
+    o = oracle.assess(oracle.layout(oracle.make_params()), pv, 10)
+    for k in ("sample", "toolow", "passed", "freq", "flags"):
+        assert (a[k] == o[k]).all(), k
+    for k in ("tmin", "tmax", "chi2", "uniformity"):
+        assert rel_err(a[k], o[k]).max() <= PV_RTOL, k
+    o8 = oracle.assess(oracle.layout(oracle.make_params()), pv[:B], 8)
+    assert (a8["freq"] == o8["freq"]).all() and rel_err(a8["uniformity"], o8["uniformity"]).max() <= PV_RTOL
+    assert lay.npv == 188
+
+
 def test_partial_test_masks(sts, oracle):
     """state->testVector subsets (the reference's -t flag) change the record layout, not the values"""
     raw = oracle.lcg_bytes(5, 2)

@@ -48,3 +48,27 @@ def test_igamc_known_values(oracle):
         assert abs(oracle.igamc(a, x) - gammaincc(a, x)) <= 2e-9 * gammaincc(a, x)
     assert oracle.igamc(3.0, 0.0) == 1.0
     assert oracle.igamc(3.0, 1e6) == 0.0
+
+
+def test_oracle_assessment_against_reference_report(oracle):
+    """oracle_assess (restating X_metrics, frequency.c:631-894) against the reference's finalAnalysisReport.txt
+    for 64 LCG streams (tests/golden/make_assess_golden.py); additivity of the tallies over shards."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "assess_lcg_64.npz"))
+    streams = 8                                      # the oracle needs ~2.5 s per stream: a prefix, then properties
+    raw = oracle.lcg_bytes(0, streams)
+    lay = oracle.layout(oracle.make_params())
+    pv, st, w, _ = oracle.run(oracle.make_params(), raw, streams, nthreads=os.cpu_count() or 1)
+    a = oracle.assess(lay, pv, 10)
+    assert (a["sample"] <= streams).all() and (a["freq"].sum(1) == a["sample"]).all()
+    assert (a["freq"] <= g["bins"]).all()            # the first 8 of the report's 64 streams
+    lo, hi = oracle.assess(lay, pv[:3], 10), oracle.assess(lay, pv[3:], 10)
+    for k in ("sample", "toolow", "freq"):
+        assert (lo[k] + hi[k] == a[k]).all()
+    # known answers: igamc(4.5, chi2 / 2) for a flat and for a one-bin histogram of 10 p-values
+    flat = np.tile((np.arange(10) + 0.5) / 10.0, (lay.npv, 1)).T.copy()
+    f = oracle.assess(lay, flat, 10)
+    e = [c for t in (12, 13) for c in range(lay.pv_off[t], lay.pv_off[t] + lay.pv_cnt[t])]
+    assert (f["freq"] == 1).all() and np.allclose(f["uniformity"], 1.0) and (f["passed"] == 10).all()
+    assert len(e) == 26
