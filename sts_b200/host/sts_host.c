@@ -6,6 +6,7 @@
  */
 #define _GNU_SOURCE
 #include <errno.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -65,7 +66,7 @@ sts_change_params(struct sts_state *s, long num, long value, double d_value)
 	case 5: s->tp.serialBlockLength = value; break;
 	case 6: s->tp.linearComplexitySequenceLength = value; break;
 	case 7: s->tp.numOfBitStreams = value; break;
-	case 8: s->tp.uniformityBins = value; break;
+	case 8: s->tp.uniformityBins = value; s->uniformityBinsFlag = true; break;
 	case 9: s->tp.n = value; break;
 	case 10: s->tp.uniformityLevel = d_value; break;
 	case 11: s->tp.alpha = d_value; break;
@@ -118,6 +119,18 @@ sts_init(struct sts_state *s)
 	if (rc != STSGPU_OK)		/* no CPU fallback: fatal, like every error in the reference */
 		sts_err(50, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(NULL));
 	stsgpu_get_layout(s->engine, &s->layout);
+	if (s->runMode == STS_MODE_ITERATE_AND_ASSESS) {
+		/* parse_args.c:791-803: bins = sqrt(iterations) unless -P 8 was given; -O forces 10 */
+		if (!s->uniformityBinsFlag)
+			s->tp.uniformityBins = (long) sqrt((double) s->tp.numOfBitStreams);
+		if (s->legacy_output)
+			s->tp.uniformityBins = 10;
+		if (s->tp.uniformityBins < 1)
+			s->tp.uniformityBins = 1;
+		rc = stsgpu_assess_begin(s->engine, s->tp.uniformityBins, s->tp.alpha, s->tp.uniformityLevel);
+		if (rc != STSGPU_OK)
+			sts_err(51, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+	}
 	for (int t = 1; t <= STS_NUMOFTESTS; t++) {
 		bool on = (s->layout.enabled_mask >> t) & 1u;
 		if (s->testVector[t] && !on)
@@ -346,6 +359,69 @@ sts_write_p_val_to_file(struct sts_state *s)
 	fclose(f);
 	if (rename(work, fin) < 0)
 		sts_err(232, __func__, "error in renaming %s to %s", work, fin);
+}
+
+/*
+ * metrics() (driver.c:475): the table every X_metrics prints in legacy format (e.g. frequency.c:700-735):
+ * bin counts, uniformity p-value, passCount/sampleCount, test name, one line per p-value column in test
+ * order, written to workDir/finalAnalysisReport.txt under the reference's header.  The tallies come from
+ * the GPU (stsgpu_assess_*), so no p-value has to be kept for this.
+ */
+void
+sts_metrics(struct sts_state *s)
+{
+	if (s->runMode != STS_MODE_ITERATE_AND_ASSESS)
+		return;
+	const int npv = s->layout.npv;
+	const long bins = s->tp.uniformityBins;
+	stsgpu_metric *m = calloc((size_t) npv, sizeof(*m));
+	int64_t *freq = calloc((size_t) npv * (size_t) bins, sizeof(*freq));
+	if (m == NULL || freq == NULL)
+		sts_err(52, __func__, "cannot allocate the assessment table");
+	int rc = stsgpu_assess_finish(s->engine, m, freq);
+	if (rc != STSGPU_OK)
+		sts_err(53, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+	char path[4096];
+	snprintf(path, sizeof(path), "%s/finalAnalysisReport.txt", s->workDir);
+	FILE *f = fopen(path, "w");
+	if (f == NULL)
+		sts_err(54, __func__, "cannot open %s: %s", path, strerror(errno));
+	fprintf(f, "------------------------------------------------------------------------------\n");
+	fprintf(f, "RESULTS FOR THE UNIFORMITY OF P-VALUES AND THE PROPORTION OF PASSING SEQUENCES\n");
+	fprintf(f, "------------------------------------------------------------------------------\n");
+	fprintf(f, "   generator is <%s>\n", s->randomDataPath);
+	fprintf(f, "------------------------------------------------------------------------------\n");
+	for (long i = 0; i < bins; i++) {
+		char name[32];
+		snprintf(name, sizeof(name), "C%ld", i + 1);
+		fprintf(f, "%3s ", name);
+	}
+	fprintf(f, " P-VALUE  PROPORTION  STATISTICAL TEST\n");
+	fprintf(f, "------------------------------------------------------------------------------\n");
+	for (int t = 1; t <= STS_NUMOFTESTS; t++) {
+		if (!((s->layout.enabled_mask >> t) & 1u))
+			continue;
+		for (int j = 0; j < s->layout.pv_cnt[t]; j++) {
+			const int q = s->layout.pv_off[t] + j;
+			for (long i = 0; i < bins; i++)
+				fprintf(f, "%3ld ", (long) freq[(long) q * bins + i]);
+			if ((double) m[q].sample_count / bins <= 0.0)
+				fprintf(f, "    ----    ");
+			else if (!m[q].uniformity_passed)
+				fprintf(f, " %8.6f * ", m[q].uniformity);
+			else
+				fprintf(f, " %8.6f   ", m[q].uniformity);
+			if (m[q].sample_count == 0)
+				fprintf(f, " ------     %s\n", sts_testNames[t]);
+			else if (!m[q].proportion_passed)
+				fprintf(f, "%4ld/%-4ld *\t %s\n", (long) m[q].pass_count, (long) m[q].sample_count, sts_testNames[t]);
+			else
+				fprintf(f, "%4ld/%-4ld\t %s\n", (long) m[q].pass_count, (long) m[q].sample_count, sts_testNames[t]);
+		}
+	}
+	fclose(f);
+	free(m);
+	free(freq);
 }
 
 void

@@ -62,6 +62,8 @@ struct sts_state {
 	int device;				/* CUDA device ordinal (new: -D, default 0) */
 	long reportCycle;			/* -I */
 	int debuglevel;				/* -v */
+	bool legacy_output;			/* -O: 10 uniformity bins, finalAnalysisReport.txt (parse_args.c:585, :792-803) */
+	bool uniformityBinsFlag;		/* -P 8 given (parse_args.c:993) */
 	char *workDir;				/* -w */
 	char *randomDataPath;			/* data file */
 	FILE *streamFile;
@@ -93,6 +95,8 @@ struct sts_driver {		/* driver.c:55-61 */
 };
 extern const struct sts_driver sts_testDriver[STS_NUMOFTESTS + 1];
 extern const char *const sts_testNames[STS_NUMOFTESTS + 1];
+/* metrics() for the uniformity / proportion table (driver.c:475, X_metrics): tallied on the GPU */
+void sts_metrics(struct sts_state *s);
 
 void sts_defaultstate(struct sts_state *state);				/* parse_args.c:55-290 defaults */
 void sts_change_params(struct sts_state *state, long num, long value, double d_value);	/* parse_args.c:960 */

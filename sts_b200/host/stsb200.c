@@ -13,9 +13,10 @@
 
 static const char *usage =
 	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
-	"               [-I reportCycle] [-w workDir] [-F r|a] [-j jobnum] [-m b|i] [-T threads] [-B batch] [-D device] datafile\n"
+	"               [-I reportCycle] [-O] [-w workDir] [-F r|a] [-j jobnum] [-m b|i] [-T threads] [-B batch] [-D device] datafile\n"
 	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
-	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues;\n"
+	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b also writes the\n"
+	"  uniformity / proportion table of the reference's legacy report (finalAnalysisReport.txt), tallied on the GPU;\n"
 	"  assess with the reference: sts -m a -d workDir -i <total iterations> ...\n";
 
 int
@@ -25,7 +26,7 @@ main(int argc, char **argv)
 	sts_defaultstate(&st);
 	int opt;
 	char *brkt, *phrase;
-	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:h")) != -1) {
+	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:Oh")) != -1) {
 		switch (opt) {
 		case 'v': st.debuglevel = atoi(optarg); break;
 		case 't':
@@ -75,6 +76,7 @@ main(int argc, char **argv)
 		case 'T': st.numberOfThreads = atol(optarg); break;
 		case 'B': st.batchStreams = atol(optarg); break;
 		case 'D': st.device = atoi(optarg); break;
+		case 'O': st.legacy_output = true; break;
 		case 'h':
 		default:
 			fputs(usage, stderr);
@@ -94,6 +96,7 @@ main(int argc, char **argv)
 	sts_init(&st);
 	sts_invokeTestSuite(&st);
 	sts_write_p_val_to_file(&st);
+	sts_metrics(&st);			/* -m b: the uniformity / proportion table, tallied on the GPU */
 	if (st.debuglevel > 0) {
 		for (int t = 1; t <= STS_NUMOFTESTS; t++)
 			if (st.testVector[t])

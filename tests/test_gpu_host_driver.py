@@ -73,6 +73,26 @@ def test_result_txt_identical_to_reference(lcg8, tmp_path):
     assert a == b
 
 
+def table_lines(path):
+    import re
+    return [l.rstrip() for l in open(path) if re.search(r"\d+/\d+\s", l) and "generator" not in l]
+
+
+def test_legacy_assessment_table_identical_to_reference(tmp_path, oracle):
+    """stsb200 -O -m b: the uniformity / proportion table (tallied on the GPU, stsgpu_assess_*) is, line for
+    line, the table of the reference's own finalAnalysisReport.txt for the same 32 streams"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    p = str(tmp_path / "lcg32.bin")
+    oracle.lcg_bytes(0, 32).tofile(p)
+    run([STSB200, "-O", "-m", "b", "-i", "32", "-F", "r", "-B", "12", "-w", str(tmp_path / "gpu"), p])
+    run([REF, "-v", "0", "-O", "-i", "32", "-F", "r", "-w", str(tmp_path / "ref"), p])
+    a = table_lines(str(tmp_path / "gpu" / "finalAnalysisReport.txt"))
+    b = table_lines(str(tmp_path / "ref" / "finalAnalysisReport.txt"))
+    assert len(a) == len(b) == 188
+    assert a == b
+
+
 def test_jobnum_and_ascii_input(lcg8, tmp_path, oracle):
     w = str(tmp_path / "j")
     run([STSB200, "-m", "i", "-i", "4", "-j", "1", "-t", "1,3,8,15", "-w", w, lcg8])   # second half of the file
