@@ -236,6 +236,11 @@ def main():
     for d in range(DEPTH):
         eng.wait()
 
+    # assessment tallies on the device (stsgpu_assess_*): every step below also adds its 1024 x 188 p-values
+    # to the per-column uniformity / proportion tallies; they are summed over ranks and judged after the timing
+    BINS = 32
+    eng.assess_begin(BINS)
+
     def finish_one(sink=None):
         eng.wait()
         if sink is not None:
@@ -303,6 +308,18 @@ def main():
     h2d = B * N_BITS // 8
     d2h = B * (lay.npv * 8 + lay.nst * 8 + lay.nw * 4)
 
+    # ---- assessment: one all-reduce of 188 x 34 counters, then the verdicts (igamc on the device) ----
+    eng.assess_reduce()
+    tallied = int(eng.assess_finish()["sample"][lay.pv_off[1]])	# every step above was tallied (the same streams again and again)
+    eng.assess_begin(BINS)					# verdicts over distinct streams: one batch per rank, sqrt(1024) = 32 bins
+    eng.submit_resident(B, rank * B)
+    eng.wait()
+    eng.assess_reduce()
+    verdict = eng.assess_finish()
+    assessment = {"uniformity_bins": BINS, "columns": int(lay.npv), "streams_tallied_in_timed_steps": tallied,
+                  "streams_assessed": int(verdict["sample"][lay.pv_off[1]]),
+                  "columns_passing_uniformity_and_proportion": int((verdict["flags"] == 3).sum())}
+
     # ---- per-group durations with every group alone on the GPU (CUDA events, serialised pass) ----
     ktimes = {}
     eng.set_profiling(1)
@@ -366,6 +383,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "assessment": assessment,
         }
         print(json.dumps(line))
     for pb in pinned:

@@ -29,6 +29,12 @@ def _worker(rank, world, port, total, out):
     dist.gather(t, gathered, dst=0)
     if rank == 0:
         np.save(out, torch.cat(gathered, 0).numpy())
+    # the assessment needs no gather at all: per-column tallies are additive, one small all-reduce
+    a = O.assess(lay, pv, 4)
+    tally = torch.from_numpy(np.concatenate([a["sample"][:, None], a["toolow"][:, None], a["freq"]], axis=1).copy())
+    dist.all_reduce(tally, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        np.save(out + ".tally.npy", tally.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,3 +52,6 @@ def test_two_rank_sharding_matches_single_process(tmp_path, oracle):
     prm = oracle.make_params(n=n, apen_m=5, serial_m=8)
     pv, st, w, lay = oracle.run(prm, oracle.lcg_bytes(0, total, n), total, nthreads=2)
     assert got.shape == pv.shape and (got == pv).all()
+    a = oracle.assess(lay, pv, 4)
+    tally = np.load(out + ".tally.npy")
+    assert (tally[:, 0] == a["sample"]).all() and (tally[:, 1] == a["toolow"]).all() and (tally[:, 2:] == a["freq"]).all()
