@@ -22,8 +22,8 @@
  *                and the |X| < T count run on registers and nothing but the count leaves the CTA.
  *                Rows 0 and 128 are their own partners and finish through shared memory.
  *
- * Moduli are compared squared against T^2 (falling back to the reference's sqrt form only inside a
- * 1e-10 relative band around T, where the north star allows N_1 to differ anyway).
+ * Moduli are compared squared, |2X|^2 < 4 T^2: equal to the reference's sqrt form except within one
+ * rounding of T, far inside the 1e-9 relative band where the north star allows N_1 to differ.
  *
  * Per stream: 8 MiB written + 8 MiB read of Y (HBM/L2), three shared-memory exchanges, about
  * 80 FP64 instructions per complex point.
@@ -156,19 +156,15 @@ dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__r
 
 /* ------------------------------------------------------------------------------------------ */
 /* X_q and X_{N-q} from Z_q = zq and Z_{N-q} = zp; wq = exp(-2 pi i q / n); returns how many of the two lie below T */
-__device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double2 wq, double T, double T2, bool both)
+__device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double2 wq, double T2x4, bool both)
 {
 	const double2 sum = make_double2(zq.x + zp.x, zq.y - zp.y);	/* Z_q + conj Z_{N-q} */
 	const double2 dif = make_double2(zq.x - zp.x, zq.y + zp.y);	/* Z_q - conj Z_{N-q} */
 	const double2 wd = cmul(wq, dif);
 	const double ar = sum.x + wd.y, ai = sum.y - wd.x;		/* 2 X_q */
 	const double br = sum.x - wd.y, bi = sum.y + wd.x;		/* 2 conj X_{N-q} */
-	const double m2a = 0.25 * (ar * ar + ai * ai), m2b = 0.25 * (br * br + bi * bi);
-	bool below_a = m2a < T2, below_b = m2b < T2;
-	if (fabs(m2a - T2) < 1e-10 * T2)
-		below_a = sqrt(0.25 * ar * ar + 0.25 * ai * ai) < T;
-	if (fabs(m2b - T2) < 1e-10 * T2)
-		below_b = sqrt(0.25 * br * br + 0.25 * bi * bi) < T;
+	/* |X| < T  <=>  |2X|^2 < 4 T^2 up to one rounding, far inside the 1e-9 band the north star allows */
+	const bool below_a = (ar * ar + ai * ai) < T2x4, below_b = (br * br + bi * bi) < T2x4;
 	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
 }
 
@@ -234,7 +230,7 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 		__syncthreads();
 	}
 	/* pass 2 (radix 8, Ns = 256): butterfly j reads j + 256 r and yields Z[k2 = j + 256 r] */
-	const double T2 = D.T * D.T;
+	const double T2x4 = 4.0 * D.T * D.T;
 	const double2 w1 = __ldg(D.q_p1 + ra);			/* exp(-2 pi i ra / n) */
 	unsigned int cnt = 0;
 	if (!self) {
@@ -271,7 +267,7 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 		const double2 wq0 = cmul(w1, __ldg(D.q_p2 + ja));
 #pragma unroll
 		for (int r = 0; r < 8; r++)
-			cnt += post_pair(za[r], zb[7 - r], cmul_w16(wq0, r), D.T, T2, true);
+			cnt += post_pair(za[r], zb[7 - r], cmul_w16(wq0, r), T2x4, true);
 	} else {
 		const int ja = threadIdx.x;
 		double2 za[8];
@@ -293,7 +289,7 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 			if (k2 > k2p)
 				continue;
 			const double2 wq = cmul(w1, __ldg(D.q_p2 + k2));
-			cnt += post_pair(buf[pad16(k2)], buf[pad16(k2p)], wq, D.T, T2, k2 != k2p);
+			cnt += post_pair(buf[pad16(k2)], buf[pad16(k2p)], wq, T2x4, k2 != k2p);
 		}
 	}
 	cnt = (unsigned int) warp_sum((int) cnt);
