@@ -197,6 +197,90 @@ lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__res
 	}
 }
 
+/*
+ * Long blocks (M > 1022, up to the reference's limit of 5000): one block per WARP, lane l holding words
+ * [l WPL, (l + 1) WPL) of the three arrays in registers.  With one block per warp the discrepancy and the
+ * length test are warp-uniform, so the updates are real (uniform) branches instead of masks: a step is
+ * WPL AND-XORs, one redux.sync, WPL funnel shifts and one shuffle for the bit that crosses lanes.
+ * (The per-thread local-memory kernel below took 83 % of a BASELINE config 4 batch.)
+ */
+template <int WPL>
+__global__ void __launch_bounds__(LC_THREADS)
+lc_kernel_warp(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
+	       long long *__restrict__ st)
+{
+	__shared__ unsigned int cls[7];
+	const int64_t s = blockIdx.x;
+	const int lane = threadIdx.x & 31;
+	if (threadIdx.x < 7)
+		cls[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int M = (int) P.lc_M;
+	const int64_t blk = (int64_t) blockIdx.y * (LC_THREADS / 32) + (threadIdx.x >> 5);
+	if (blk < P.lc_N) {				/* warp-uniform */
+		const int64_t start = blk * M;
+		uint32_t S[WPL], C[WPL], B[WPL];
+#pragma unroll
+		for (int j = 0; j < WPL; j++) {
+			const int i = lane * WPL + j;		/* word index; array index k <-> position k - 1 */
+			uint32_t v = 0;
+			const int valid = M + 1 - 32 * i;	/* indices still inside the block */
+			if (valid > 0) {
+				v = (i == 0) ? (get32(w, start) >> 1) : get32(w, start + 32 * (int64_t) i - 1);
+				if (valid < 32)
+					v &= mask_below((uint32_t) valid);
+			}
+			S[j] = v;
+			C[j] = 0;
+			B[j] = 0;
+		}
+		if (lane == 0) {
+			C[0] = 0x40000000u;	/* c_0 at position 0  (index 1) */
+			B[0] = 0x80000000u;	/* b_0 at position -1 (index 0) */
+		}
+		int L = 0;
+		for (int N = 0; N < M; N++) {
+			uint32_t acc = 0;
+#pragma unroll
+			for (int j = 0; j < WPL; j++)
+				acc ^= C[j] & S[j];
+			const uint32_t d = (uint32_t) __popc(__reduce_xor_sync(0xffffffffu, acc)) & 1u;
+			if (d) {				/* linearComplexity.c:322-336 */
+				if (2 * L <= N) {
+#pragma unroll
+					for (int j = 0; j < WPL; j++) {
+						const uint32_t c_old = C[j];
+						C[j] = c_old ^ B[j];
+						B[j] = c_old;
+					}
+					L = N + 1 - L;
+				} else {
+#pragma unroll
+					for (int j = 0; j < WPL; j++)
+						C[j] ^= B[j];
+				}
+			}
+			/* advance to N + 1: shift the whole array by one position */
+			uint32_t carry = __shfl_up_sync(0xffffffffu, C[WPL - 1], 1);
+			if (lane == 0)
+				carry = 0;
+#pragma unroll
+			for (int j = 0; j < WPL; j++) {
+				const uint32_t c = C[j];
+				C[j] = (c >> 1) | (carry << 31);
+				carry = c;
+			}
+		}
+		if (lane == 0)
+			atomicAdd(&cls[class_lut[L]], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 7 && cls[threadIdx.x])
+		atomicAdd((unsigned long long *) (st + s * P.nst + P.st_off[STSGPU_TEST_LINEARCOMPLEXITY] + threadIdx.x),
+			  (unsigned long long) cls[threadIdx.x]);
+}
+
 /* any M up to 5000: the same recurrence with the arrays in (L1-resident) local memory */
 #define LC_MAXW 160
 __global__ void __launch_bounds__(LC_THREADS)
@@ -278,7 +362,19 @@ cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_c
 	} else if (W <= 32) {
 		lc_kernel_reg<32><<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
 	} else {
-		lc_kernel_generic<<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		/* one block per warp, ceil(W / 32) words per lane (W <= 157 at M = 5000) */
+		dim3 gw((unsigned) L.nstreams, (unsigned) ((P.lc_N + LC_THREADS / 32 - 1) / (LC_THREADS / 32)));
+		const int wpl = (W + 31) / 32;
+		if (wpl <= 2)
+			lc_kernel_warp<2><<<gw, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		else if (wpl == 3)
+			lc_kernel_warp<3><<<gw, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		else if (wpl == 4)
+			lc_kernel_warp<4><<<gw, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		else if (wpl == 5)
+			lc_kernel_warp<5><<<gw, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
+		else
+			lc_kernel_generic<<<grid, LC_THREADS, 0, L.stream>>>(P, L.d_in, d_class_lut, L.d_st);
 	}
 	return cudaGetLastError();
 }
