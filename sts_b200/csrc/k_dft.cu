@@ -30,7 +30,7 @@
 
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 
-#define GDFT_THREADS 256
+#define GDFT_THREADS 512
 
 template <> __device__ __forceinline__ void bfly<3>(double2 *v)
 {
