@@ -53,6 +53,16 @@ for r in rows[2:]:
         a[key] += f(r, met) * us
     a["regs"] = int(f(r, "launch__registers_per_thread"))
 
+# launches of each kernel in ONE batch of B streams (the capture window may straddle two batches: every kernel is
+# scaled to its per-batch launch count, i.e. average launch x launches per batch)
+per_batch = {"dft_cols16": max(1, B // 128), "dft_rows16": max(1, B // 128)}
+for name, a in agg.items():
+    want = per_batch.get(name, 1)
+    if a["n"] != want:
+        k = want / a["n"]
+        for key in ("us", "rd", "wr", "alu", "fp64", "lsu", "issue", "occ"):
+            a[key] *= k
+        a["n"] = want
 stream_bytes = n // 8
 alg = {  # algorithmic bytes per stream of one launch of the kernel
     "dft_cols16": stream_bytes + 16 * (n // 2), "dft_rows16": 16 * (n // 2),
