@@ -55,12 +55,13 @@ nonoverlapping_kernel(DevParams P, const uint32_t *__restrict__ in, const uint32
 		const int64_t j0 = g * 32;
 		uint32_t cur = get32(w, start + j0), nxt = get32(w, start + j0 + 32);
 		int cnt = (last - j0 >= 31) ? 32 : (int) (last - j0 + 1);
-#pragma unroll 8
-		for (int p = 0; p < 32; p++) {
-			if (p < cnt) {
-				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - m);
-				atomicAdd(&hist[v], 1u);
-			}
+		if (cnt == 32) {			/* the common case without a test per window */
+#pragma unroll
+			for (int p = 0; p < 32; p++)
+				atomicAdd(&hist[__funnelshift_l(nxt, cur, p) >> (32 - m)], 1u);
+		} else {
+			for (int p = 0; p < cnt; p++)
+				atomicAdd(&hist[__funnelshift_l(nxt, cur, p) >> (32 - m)], 1u);
 		}
 	}
 	__syncthreads();
@@ -196,9 +197,15 @@ cyclic_hist_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__re
 			nxt = cyc32(w, j0 + 32, n);
 		}
 		int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
+		if (cnt == 32) {
 #pragma unroll 8
-		for (int p = 0; p < 32; p++) {
-			if (p < cnt) {
+			for (int p = 0; p < 32; p++) {
+				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
+				if ((v >> B) == slice)
+					atomicAdd(&hist[v & lmask], 1u);
+			}
+		} else {
+			for (int p = 0; p < cnt; p++) {
 				uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
 				if ((v >> B) == slice)
 					atomicAdd(&hist[v & lmask], 1u);
@@ -252,11 +259,16 @@ cyclic_hist16_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__
 			nxt = cyc32(w, j0 + 32, n);
 		}
 		const int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);
-#pragma unroll 8
-		for (int p = 0; p < 32; p++) {
-			if (p < cnt) {
+		if (cnt == 32) {			/* the common case without a test per window */
+#pragma unroll
+			for (int p = 0; p < 32; p++) {
 				const uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
-				atomicAdd(&hist[v >> 1], (v & 1u) ? 0x10000u : 1u);
+				atomicAdd(&hist[v >> 1], 1u << ((v & 1u) << 4));
+			}
+		} else {
+			for (int p = 0; p < cnt; p++) {
+				const uint32_t v = __funnelshift_l(nxt, cur, p) >> (32 - H);
+				atomicAdd(&hist[v >> 1], 1u << ((v & 1u) << 4));
 			}
 		}
 	}
