@@ -11,9 +11,9 @@
  *   - looks the term up in a table log2tab[d] = log(d) / log(2.0) computed ON THE HOST with the
  *     reference's expression and libm, so each addend is the reference's double;
  *   - reproduces the sequential round-to-nearest-even accumulation EXACTLY but in parallel
- *     (rne_sum.cuh): 128 terms (4 rows) at a time as composable integer maps; a group that would
- *     leave the binade of the running sum (about 14 of 1010 groups at L = 7) is added term by term
- *     with DADD in block order instead.
+ *     (rne_sum.cuh): the up to 1024 terms of a super row as composable integer maps, each lane
+ *     composing a contiguous span, one butterfly per super row; a super row in which the running
+ *     sum changes binade (about 14 of 127 at L = 7) is added term by term with DADD instead.
  *
  * One warp per stream (one CTA = one warp).  The packed stream is staged through shared memory in
  * "super rows" of 32 L words = 1024 blocks with cp.async, double buffered, so DRAM latency is off
@@ -41,8 +41,8 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 	extern __shared__ __align__(16) uint32_t usm[];
 	const int L = P.univ_L;
 	const int IB = 32 * L + 2;				/* one super row + pad word, even */
-	double *tbuf = (double *) usm;				/* [UNI_GROUP * 32] terms in block order */
-	uint32_t *ibuf = usm + 2 * UNI_GROUP * 32;		/* [2][IB] staged input */
+	double *tbuf = (double *) usm;				/* [32][33] terms of one super row, block order */
+	uint32_t *ibuf = usm + 2 * 32 * 33;			/* [2][IB] staged input */
 	uint32_t *T = ibuf + 2 * IB;				/* [2^L] */
 	const int64_t s = blockIdx.x;
 	const int lane = threadIdx.x;
@@ -79,6 +79,7 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 		__syncwarp();
 		const uint32_t *buf = ibuf + (sr & 1) * IB;
 		const int row_end = min(32, rows - sr * 32);
+		const int first_test = min(row_end, max(0, qrows - sr * 32));	/* first row of this super row that is summed */
 		for (int rg = 0; rg < row_end; rg += UNI_GROUP) {
 			const int row0 = sr * 32 + rg;
 			const bool testing = row0 >= qrows;
@@ -103,7 +104,7 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 					T[v[r4]] = (uint32_t) (row0 + r4) * 32u + lane + 1u;	/* 1-based block number */
 				__syncwarp();
 			}
-			/* phase C: distances -> terms, in block order in tbuf */
+			/* phase C: distances -> terms, in block order in tbuf (rows of 32, pitch 33) */
 			if (testing) {
 				double term[UNI_GROUP];
 #pragma unroll
@@ -112,21 +113,31 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 					const uint32_t prev = lower[r4] ? (i - lane + (31 - __clz(lower[r4]))) : tprev[r4];
 					term[r4] = __ldg(log2tab + (i - prev));
 				}
+				const int trow = rg - first_test;	/* row inside this super row's test span */
 #pragma unroll
 				for (int r4 = 0; r4 < UNI_GROUP; r4++)
-					tbuf[r4 * 32 + lane] = term[r4];
-				__syncwarp();
+					tbuf[(trow + r4) * 33 + lane] = term[r4];
 			}
-			if (!testing)
-				continue;
-			/* universal.c:369: sequential accumulation in block order, reproduced exactly */
-			const double4 ta = *(const double4 *) (tbuf + 4 * lane);
-			if (!warp_rne_sum128(sum, ta, lane)) {
+		}
+		/* universal.c:369: sequential accumulation in block order, reproduced exactly, one super row at a time */
+		const int nrows_t = row_end - first_test;
+		if (nrows_t > 0) {
+			__syncwarp();
+			if (!warp_rne_sum_rows(sum, tbuf, nrows_t, lane)) {
+				/* a binade change inside this super row: retry 128 terms at a time, then term by term */
+				for (int r = 0; r < nrows_t; r += UNI_GROUP) {
+					const double *tb = tbuf + (r + (lane >> 3)) * 33 + 4 * (lane & 7);
+					const double4 t4 = make_double4(tb[0], tb[1], tb[2], tb[3]);
+					if (!warp_rne_sum128(sum, t4, lane)) {
+						for (int rr = r; rr < r + UNI_GROUP; rr++) {
 #pragma unroll 8
-				for (int j = 0; j < UNI_GROUP * 32; j++)
-					sum += tbuf[j];
+							for (int j = 0; j < 32; j++)
+								sum += tbuf[rr * 33 + j];
+						}
+					}
+				}
 			}
-			__syncwarp();				/* tbuf is rewritten by the next group */
+			__syncwarp();				/* tbuf is rewritten by the next super row */
 		}
 	}
 	if (lane == 0)
@@ -137,7 +148,7 @@ cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const doubl
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_UNIVERSAL)))
 		return cudaSuccess;
-	const size_t smem = sizeof(uint32_t) * ((size_t) 2 * UNI_GROUP * 32 + 2 * (32 * P.univ_L + 2) + ((size_t) 1 << P.univ_L));
+	const size_t smem = sizeof(uint32_t) * ((size_t) 2 * 32 * 33 + 2 * (32 * P.univ_L + 2) + ((size_t) 1 << P.univ_L));
 	cudaError_t e = cudaFuncSetAttribute(universal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
 	if (e != cudaSuccess)
 		return e;

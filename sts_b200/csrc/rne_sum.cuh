@@ -94,3 +94,48 @@ __device__ __forceinline__ bool warp_rne_sum128(double &sum, const double4 &t, i
 	sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) | (Snew & 0x000FFFFFFFFFFFFFull)));
 	return true;
 }
+
+/*
+ * The same for 32 * nrows terms kept in shared memory as rows of 32 with a pitch of 33 doubles (term i at
+ * tb[(i / 32) * 33 + i % 32]): lane l composes the nrows consecutive terms [l nrows, (l + 1) nrows) one after
+ * the other (decode + compose, about 40 integer instructions per term and no cross-lane traffic), then ONE
+ * butterfly merges the 32 spans.  Returns false (sum untouched) when the terms are not two binades below the
+ * sum or the sum would leave its binade: the caller then adds the terms one by one.
+ */
+__device__ __forceinline__ bool warp_rne_sum_rows(double &sum, const double *tb, int nrows, int lane)
+{
+	const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
+	const int k = (int) (sb >> 52) - 1023;
+	if (k < -1000)
+		return false;
+	RneMap f;
+	f.a0 = 0;
+	f.dl = 0;
+	unsigned int himax = 0;
+	for (int j = 0; j < nrows; j++) {
+		const int i = lane * nrows + j;
+		const double x = tb[(i >> 5) * 33 + (i & 31)];
+		const unsigned int hi = (unsigned int) __double2hiint(x);
+		himax = max(himax, hi);
+		/* a term too large for this binade is caught below; keep the shift in range meanwhile */
+		f = rne_compose(f, rne_of_term(x, max(k, (int) (hi >> 20) - 1023 + 2)));
+	}
+	himax = __reduce_max_sync(0xffffffffu, himax);
+	if (k < (int) (himax >> 20) - 1023 + 2)
+		return false;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		RneMap g;
+		const uint32_t plo = __shfl_xor_sync(0xffffffffu, (uint32_t) f.a0, o);
+		const uint32_t phi = __shfl_xor_sync(0xffffffffu, (uint32_t) (f.a0 >> 32) | ((uint32_t) (f.dl + 1) << 30), o);
+		g.a0 = ((unsigned long long) (phi & 0x3FFFFFFFu) << 32) | plo;
+		g.dl = (int) (phi >> 30) - 1;
+		f = (lane & o) ? rne_compose(g, f) : rne_compose(f, g);
+	}
+	const unsigned long long S = (sb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+	const unsigned long long Snew = S + ((S & 1ull) ? f.a0 + (long long) f.dl : f.a0);
+	if (Snew >= 0x0020000000000000ull)		/* would leave the binade */
+		return false;
+	sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) | (Snew & 0x000FFFFFFFFFFFFFull)));
+	return true;
+}
