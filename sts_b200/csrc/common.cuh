@@ -144,5 +144,5 @@ cudaError_t launch_blocks(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_rank(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_nonoverlapping(const DevParams &P, const LaunchCtx &L, const uint32_t *d_templates);
 cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist, uint32_t *d_flags);
-cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const double *d_log2_table);
+cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const unsigned long long *d_log2_table);
 cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_class_lut);

@@ -409,10 +409,16 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	if (en & (1u << STSGPU_TEST_UNIVERSAL)) {
 		/* universal.c:369: log(i - T[.]) / log(2), one table entry per possible distance */
 		const int64_t cnt = P.univ_Q + P.univ_K + 1;
-		std::vector<double> tab((size_t) cnt);
-		tab[0] = 0.0;
-		for (int64_t d = 1; d < cnt; d++)
-			tab[d] = log((double) d) / K.log2_;
+		/* stored as the exact fixed point value x * 2^58: every x is 0 or a double in [1, 32) (k_universal.cu) */
+		std::vector<unsigned long long> tab((size_t) cnt);
+		tab[0] = 0;
+		for (int64_t d = 1; d < cnt; d++) {
+			const double x = log((double) d) / K.log2_;
+			const double scaled = ldexp(x, 58);
+			if (!(x == 0.0 || (x >= 1.0 && x < 32.0)) || scaled != floor(scaled))
+				return fail_create(ctx, STSGPU_E_UNSUPPORTED, "Universal: log2 table value outside the fixed point range");
+			tab[d] = (unsigned long long) scaled;
+		}
 		CKC(upload(&ctx->d_log2tab, tab.data(), tab.size()), "upload(log2 table)");
 	}
 	if (en & (1u << STSGPU_TEST_DFT)) {

@@ -63,7 +63,7 @@ struct stsgpu_ctx {
 
 	uint32_t *d_templates = nullptr;
 	uint8_t *d_class_lut = nullptr;
-	double *d_log2tab = nullptr;
+	unsigned long long *d_log2tab = nullptr;	/* log(d) / log(2) as exact fixed point x * 2^58 */
 	double2 *dft_tabs[12] = { nullptr };
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;

@@ -8,12 +8,16 @@
  *     (one "row"), `match.any` resolves repeats inside the row and a shared-memory table T[2^L]
  *     carries the last occurrence across rows (table starts at 0 like the reference's memset,
  *     universal.c:327);
- *   - looks the term up in a table log2tab[d] = log(d) / log(2.0) computed ON THE HOST with the
- *     reference's expression and libm, so each addend is the reference's double;
+ *   - looks the term up in a table of log(d) / log(2.0) computed ON THE HOST with the reference's
+ *     expression and libm, so each addend is the reference's double - stored as the exact fixed
+ *     point value x * 2^58 (every term is a double in [1, 32) or 0), which is what the integer
+ *     emulation of the sum needs;
  *   - reproduces the sequential round-to-nearest-even accumulation EXACTLY but in parallel
- *     (rne_sum.cuh): the up to 1024 terms of a super row as composable integer maps, each lane
- *     composing a contiguous span, one butterfly per super row; a super row in which the running
- *     sum changes binade (about 14 of 127 at L = 7) is added term by term with DADD instead.
+ *     (rne_sum.cuh): while the running sum stays in one binade and no addend is an exact tie,
+ *     adding the up to 1024 terms of a super row is a plain integer sum of rounded fixed point
+ *     values, each lane summing a contiguous span; a super row with a tie or a binade change
+ *     (about 10 of 127 at L = 7) goes through composable round-to-even maps, 128 terms at a time,
+ *     and at worst term by term with DADD.
  *
  * One warp per stream (one CTA = one warp).  The packed stream is staged through shared memory in
  * "super rows" of 32 L words = 1024 blocks with cp.async, double buffered, so DRAM latency is off
@@ -35,13 +39,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(32)
-universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__restrict__ log2tab,
+universal_kernel(DevParams P, const uint32_t *__restrict__ in, const unsigned long long *__restrict__ log2fix,
 		 long long *__restrict__ st)
 {
 	extern __shared__ __align__(16) uint32_t usm[];
 	const int L = P.univ_L;
 	const int IB = 32 * L + 2;				/* one super row + pad word, even */
-	double *tbuf = (double *) usm;				/* [32][33] terms of one super row, block order */
+	unsigned long long *tbuf = (unsigned long long *) usm;	/* [32][33] terms of one super row as fixed point, block order */
 	uint32_t *ibuf = usm + 2 * 32 * 33;			/* [2][IB] staged input */
 	uint32_t *T = ibuf + 2 * IB;				/* [2^L] */
 	const int64_t s = blockIdx.x;
@@ -106,12 +110,12 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 			}
 			/* phase C: distances -> terms, in block order in tbuf (rows of 32, pitch 33) */
 			if (testing) {
-				double term[UNI_GROUP];
+				unsigned long long term[UNI_GROUP];
 #pragma unroll
 				for (int r4 = 0; r4 < UNI_GROUP; r4++) {
 					const uint32_t i = (uint32_t) (row0 + r4) * 32u + lane + 1u;
 					const uint32_t prev = lower[r4] ? (i - lane + (31 - __clz(lower[r4]))) : tprev[r4];
-					term[r4] = __ldg(log2tab + (i - prev));
+					term[r4] = __ldg(log2fix + (i - prev));
 				}
 				const int trow = rg - first_test;	/* row inside this super row's test span */
 #pragma unroll
@@ -123,16 +127,17 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 		const int nrows_t = row_end - first_test;
 		if (nrows_t > 0) {
 			__syncwarp();
-			if (!warp_rne_sum_rows(sum, tbuf, nrows_t, lane)) {
-				/* a binade change inside this super row: retry 128 terms at a time, then term by term */
+			if (!warp_rne_sum_rows_fixed(sum, tbuf, nrows_t, lane)) {
+				/* a tie or a binade change inside this super row: composable maps on 128 terms at a time, then term by term */
 				for (int r = 0; r < nrows_t; r += UNI_GROUP) {
-					const double *tb = tbuf + (r + (lane >> 3)) * 33 + 4 * (lane & 7);
-					const double4 t4 = make_double4(tb[0], tb[1], tb[2], tb[3]);
+					const unsigned long long *tb = tbuf + (r + (lane >> 3)) * 33 + 4 * (lane & 7);
+					const double4 t4 = make_double4(rne_fixed_to_double(tb[0]), rne_fixed_to_double(tb[1]),
+									rne_fixed_to_double(tb[2]), rne_fixed_to_double(tb[3]));
 					if (!warp_rne_sum128(sum, t4, lane)) {
 						for (int rr = r; rr < r + UNI_GROUP; rr++) {
 #pragma unroll 8
 							for (int j = 0; j < 32; j++)
-								sum += tbuf[rr * 33 + j];
+								sum += rne_fixed_to_double(tbuf[rr * 33 + j]);
 						}
 					}
 				}
@@ -144,7 +149,7 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const double *__r
 		st[s * P.nst + P.st_off[STSGPU_TEST_UNIVERSAL]] = __double_as_longlong(sum);
 }
 
-cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const double *d_log2_table)
+cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const unsigned long long *d_log2_table)
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_UNIVERSAL)))
 		return cudaSuccess;

@@ -139,3 +139,47 @@ __device__ __forceinline__ bool warp_rne_sum_rows(double &sum, const double *tb,
 	sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) | (Snew & 0x000FFFFFFFFFFFFFull)));
 	return true;
 }
+
+/*
+ * Fast path for terms kept as exact fixed point X = x * 2^RNE_FX (the Universal test's table of log2 values):
+ * away from ties, adding x to a sum in binade k is S += (X + half) >> sh with sh = k - 52 + RNE_FX, i.e. a plain
+ * integer sum, about a dozen instructions per term and one 64-bit add-reduction per 32 * nrows terms.  A tie
+ * (X mod 2^sh == half, about once per stream) or a binade change returns false with sum untouched; the caller
+ * then uses the composable maps above on those terms.  Layout as in warp_rne_sum_rows.
+ */
+#define RNE_FX 58
+__device__ __forceinline__ double rne_fixed_to_double(unsigned long long X)
+{
+	return __ull2double_rn(X) * 3.4694469519536141888e-18;		/* 2^-58; X has at most 53 significant bits: exact */
+}
+__device__ __forceinline__ bool warp_rne_sum_rows_fixed(double &sum, const unsigned long long *tb, int nrows, int lane)
+{
+	const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
+	const int k = (int) (sb >> 52) - 1023;
+	const int sh = k - 52 + RNE_FX;
+	if (sh < 1 || sh > 63)
+		return false;
+	const unsigned long long half = 1ull << (sh - 1), mask = (half << 1) - 1ull;
+	unsigned long long acc = 0;
+	bool tie = false;
+	for (int j = 0; j < nrows; j++) {
+		const int i = lane * nrows + j;
+		const unsigned long long X = tb[(i >> 5) * 33 + (i & 31)];
+		acc += (X + half) >> sh;
+		tie = tie || ((X & mask) == half);
+	}
+	if (__any_sync(0xffffffffu, tie))
+		return false;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t) acc, o);
+		const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t) (acc >> 32), o);
+		acc += ((unsigned long long) hi << 32) | lo;
+	}
+	const unsigned long long S = (sb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+	const unsigned long long Snew = S + acc;
+	if (Snew >= 0x0020000000000000ull)		/* would leave the binade */
+		return false;
+	sum = __longlong_as_double((long long) (((unsigned long long) (k + 1023) << 52) | (Snew & 0x000FFFFFFFFFFFFFull)));
+	return true;
+}
