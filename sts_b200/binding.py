@@ -275,7 +275,7 @@ class Engine:
         self._ck(self.lib.stsgpu_assess_reduce(self.h), "assess_reduce")
 
     def assess_finish(self):
-        """-> dict of per-column arrays (same keys as oracle.assess)"""
+        """-> dict of per-column arrays (one entry per p-value column, record order)"""
         npv, bins = self.layout.npv, self._assess_bins
         m = (Metric * npv)()
         freq = np.zeros((npv, bins), dtype=np.int64)
