@@ -115,6 +115,20 @@ def test_jobnum_and_ascii_input(lcg8, tmp_path, oracle):
         assert rel_err(pa[t].reshape(ref.shape), ref).max() <= 1e-9
 
 
+def test_distributed_mode_script(lcg8, tmp_path):
+    """tools/run_distributed.sh: the reference's `-m i -j K` / `-m a -d DIR` flow with one job per process; here two
+    jobs on the one GPU that is guaranteed to exist (jobs only differ in -j and -D), assessed by the reference"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    d = str(tmp_path / "dist")
+    os.makedirs(d)
+    for k in range(2):
+        run([STSB200, "-m", "i", "-D", "0", "-j", str(k), "-i", "4", "-F", "r", "-w", d, lcg8])
+    run([REF, "-v", "0", "-m", "a", "-d", d, "-i", "8", "-w", str(tmp_path / "assess")])
+    run([REF, "-v", "0", "-i", "8", "-T", "8", "-F", "r", "-w", str(tmp_path / "ref"), lcg8])
+    assert result_body(str(tmp_path / "assess" / "result.txt")) == result_body(str(tmp_path / "ref" / "result.txt"))
+
+
 def test_short_file_is_fatal(tmp_path):
     p = str(tmp_path / "short.bin")
     open(p, "wb").write(b"\x00" * 1000)
