@@ -254,6 +254,42 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     assert lay.npv == 188
 
 
+@pytest.mark.parametrize("test,prm", [
+    (15, dict(n=1 << 20, linear_complexity_M=1100)),     # LinearComplexity: warp-per-block kernel, 2 words per lane
+    (15, dict(n=1 << 20, linear_complexity_M=2048)),     # ... 3 words per lane (W = 65)
+    (15, dict(n=1 << 20, linear_complexity_M=3100)),     # ... 4
+    (15, dict(n=1 << 20, linear_complexity_M=4100)),     # ... 5
+    (15, dict(n=1 << 20, linear_complexity_M=1022)),     # last M of the per-thread register kernel (W = 32)
+    (15, dict(n=1 << 20, linear_complexity_M=511)),      # last M of the windowed kernel (W = 16)
+    (10, dict(n=2200000)),                               # Universal L = 8
+    (10, dict(n=904960)),                                # Universal L = 7 at its smallest n
+    (14, dict(n=1 << 18, serial_m=3)),                   # Serial: smallest block length
+    (14, dict(n=1 << 18, serial_m=12)),
+    (11, dict(n=1 << 18, apen_m=1)),                     # ApEn: H = 2
+    (11, dict(n=1 << 20, apen_m=14)),                    # ApEn: H = 15
+    (14, dict(n=1 << 21, serial_m=18)),                  # Serial: sliced 32-bit histogram, 8 slices
+    (8, dict(n=1 << 18, non_overlapping_m=8)),
+    (8, dict(n=1 << 18, non_overlapping_m=12)),
+    (2, dict(n=1 << 20, block_frequency_M=11000)),       # blocks that are not word aligned
+    (7, dict(n=1 << 14)),                                # DFT: generic path, small power of two
+    (7, dict(n=5 * (1 << 16))),                          # DFT: one radix-5 pass
+    (7, dict(n=1 << 22)),                                # DFT: generic path above the fast kernel's length
+])
+def test_single_test_parameter_sweep(sts, oracle, test, prm):
+    """kernel variants the default parameters never reach, one test at a time, bit-exact / 1e-9 against the oracle"""
+    base = dict(n=1 << 20, block_frequency_M=16384, non_overlapping_m=9, overlapping_m=9, apen_m=10, serial_m=16,
+                linear_complexity_M=500)
+    base.update(prm)
+    if test == 2 and base["n"] // base["block_frequency_M"] >= 100:
+        pytest.skip("BlockFrequency disables itself")
+    streams, mask = 2, 1 << test
+    raw = oracle.lcg_bytes(3, streams, base["n"])
+    with sts.Engine(max_streams=streams, test_mask=mask, **base) as eng:
+        assert eng.layout.enabled_mask == mask == oracle.layout(oracle.make_params(test_mask=mask, **base)).enabled_mask
+        pv, st, w = eng.run(raw, streams)
+        compare_with_oracle(sts, oracle, eng, mask, base, raw, streams, pv, st, w)
+
+
 def test_partial_test_masks(sts, oracle):
     """state->testVector subsets (the reference's -t flag) change the record layout, not the values"""
     raw = oracle.lcg_bytes(5, 2)
