@@ -11,8 +11,11 @@ struct DftPlan {
 	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
 	int fast;		/* n = 2^20: the specialised kernels of k_dft_fast.cu */
-	const double2 *w1;	/* exp(-2 pi i e / N1), e < N1 */
-	const double2 *w2;	/* exp(-2 pi i e / N2), e < N2 */
+	/* per-pass twiddles, pass p at offset off[p]: entry (r - 1) Ns + k = exp(-2 pi i k r / (Ns R)), so that
+	 * consecutive butterflies (consecutive k) read consecutive table entries */
+	const double2 *w1;
+	const double2 *w2;
+	int off1[DFT_MAX_PASSES], off2[DFT_MAX_PASSES];
 	const double2 *tl;	/* exp(-2 pi i e / N), e < 1024 */
 	const double2 *th;	/* exp(-2 pi i 1024 e / N), e < N / 1024 + 1 */
 	const double2 *p1;	/* exp(-2 pi i k1 / n), k1 < N1 */

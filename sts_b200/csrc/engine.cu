@@ -428,8 +428,26 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		D.fast = (n == (1LL << 20)) ? 1 : 0;
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
 		std::vector<double2> w1(N1), w2(N2), tl(1024), th((size_t) (N / 1024 + 1)), p1(N1), p2(N2);
-		for (int k = 0; k < N1; k++) w1[k] = unit_root(k, N1);
-		for (int k = 0; k < N2; k++) w2[k] = unit_root(k, N2);
+		{	/* per-pass twiddle tables (dft.h): entry (r - 1) Ns + k of pass p = exp(-2 pi i k r / (Ns R)) */
+			for (int which = 0; which < 2; which++) {
+				std::vector<double2> &w = which ? w2 : w1;
+				const int np = which ? D.np2 : D.np1;
+				const int *rad = which ? D.rad2 : D.rad1;
+				int *off = which ? D.off2 : D.off1;
+				w.clear();
+				int Ns = 1;
+				for (int ps = 0; ps < np; ps++) {
+					const int R = rad[ps];
+					off[ps] = (int) w.size();
+					for (int r = 1; r < R; r++)
+						for (int k = 0; k < Ns; k++)
+							w.push_back(unit_root((long double) k * r, (long double) Ns * R));
+					Ns *= R;
+				}
+				if (w.empty())
+					w.push_back(make_double2(1.0, 0.0));
+			}
+		}
 		for (int k = 0; k < 1024; k++) tl[k] = unit_root(k, (long double) N);
 		for (size_t k = 0; k < th.size(); k++) th[k] = unit_root((long double) k * 1024, (long double) N);
 		for (int k = 0; k < N1; k++) p1[k] = unit_root(k, (long double) n);

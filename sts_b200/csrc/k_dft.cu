@@ -18,7 +18,8 @@
  *
  * Each 1-D FFT is a Stockham autosort FFT out of two shared-memory buffers (ping-pong), one pass per
  * radix of the plan (8, 5, 4, 3 or 2), a thread looping over the butterflies of the pass; twiddles
- * come from a table of the N1-th (N2-th) roots of unity computed on the host in long double.
+ * come from per-pass tables computed on the host in long double and laid out so that consecutive
+ * butterflies read consecutive entries.
  *
  * Roofline: the intermediate Y is the traffic: 16 N bytes written + 16 N bytes read per stream
  * against n/8 input bytes; FP64 work is about 5 N log2 N flop.
@@ -72,7 +73,8 @@ __device__ __forceinline__ void bfly_any(double2 *v, int R)
 /*
  * One Stockham pass of radix R over an FFT of length Nf laid out with element stride `es` (and a
  * fixed offset already folded into src/dst): butterfly b reads src[(b + r Nf/R) es], multiplies by
- * W_(Ns R)^(k r), k = b mod Ns, and writes dst[((b - k) R + k + r Ns) es].
+ * W_(Ns R)^(k r), k = b mod Ns (table of this pass: wtab[(r - 1) Ns + k]), and writes
+ * dst[((b - k) R + k + r Ns) es].
  */
 __device__ __forceinline__ void stockham_butterfly(const double2 *src, double2 *dst, int es, int Nf, int R, int Ns, int b,
 						     const double2 *__restrict__ wtab)
@@ -85,11 +87,10 @@ __device__ __forceinline__ void stockham_butterfly(const double2 *src, double2 *
 			v[r] = src[(b + r * q) * es];
 	const int k = b % Ns;
 	if (Ns > 1) {
-		const int step = Nf / (Ns * R);			/* W_(Ns R)^(k r) = W_Nf^(k r step) */
 #pragma unroll
 		for (int r = 1; r < 8; r++)
 			if (r < R)
-				v[r] = cmul(v[r], __ldg(wtab + (int64_t) k * r * step));
+				v[r] = cmul(v[r], __ldg(wtab + (r - 1) * Ns + k));
 	}
 	bfly_any(v, R);
 	const int base = (b - k) * R + k;
@@ -125,7 +126,7 @@ dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2
 		const int nb = N1 / R;
 		for (int e = threadIdx.x; e < nb * CW; e += GDFT_THREADS) {
 			const int bb = e / CW, c = e % CW;
-			stockham_butterfly(a + c, b + c, CW, N1, R, Ns, bb, D.w1);
+			stockham_butterfly(a + c, b + c, CW, N1, R, Ns, bb, D.w1 + D.off1[ps]);
 		}
 		__syncthreads();
 		double2 *t = a; a = b; b = t;
@@ -166,7 +167,7 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 		for (int e = threadIdx.x; e < rows * nb; e += GDFT_THREADS) {
 			const int r_ = e / nb, bb = e % nb;
 			double2 *base = buf + (size_t) r_ * 2 * N2;
-			stockham_butterfly(base + cur * N2, base + (cur ^ 1) * N2, 1, N2, R, Ns, bb, D.w2);
+			stockham_butterfly(base + cur * N2, base + (cur ^ 1) * N2, 1, N2, R, Ns, bb, D.w2 + D.off2[ps]);
 		}
 		__syncthreads();
 		cur ^= 1;
