@@ -364,9 +364,8 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_uni, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
-		const int prio_dft = (getenv("STSGPU_DFT_PRIO_HI") && atoi(getenv("STSGPU_DFT_PRIO_HI"))) ? prio_hi : prio_lo;
-		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_dft), "cudaStreamCreate");
-		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_dft), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join_uni, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join_dft, cudaEventDisableTiming), "cudaEventCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_dft_fork, cudaEventDisableTiming), "cudaEventCreate");
@@ -597,9 +596,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		{ "blocks(blockfreq,longestrun,overlapping)", K_LIGHT }, { "rank", K_LIGHT }, { "nonoverlapping", K_LIGHT },
 	};
 	cudaStream_t kind_stream[4] = { sl, S.s_uni, S.s_heavy, S.s_dft[0] };
-	static const bool dft_first = getenv("STSGPU_DFT_FIRST") && atoi(getenv("STSGPU_DFT_FIRST")) > 0;
-	for (int gi = 0; gi < G_COUNT; gi++) {
-		const int g = (dft_first && gi < 2) ? 1 - gi : gi;	/* experiment: launch the DFT before LinearComplexity */
+	for (int g = 0; g < G_COUNT; g++) {
 		L.stream = prof ? sl : kind_stream[groups[g].kind];
 		const int slot = S.nkernels;
 		CK(cudaEventRecord(S.k_ev0[slot], L.stream));
