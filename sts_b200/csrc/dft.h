@@ -10,6 +10,7 @@ struct DftPlan {
 	int np1, np2;
 	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
+	int threads;		/* CTA size of the generic kernels (256 or 512) */
 	int fast;		/* n = 2^20: the specialised kernels of k_dft_fast.cu */
 	/* per-pass twiddles, pass p at offset off[p]: entry (r - 1) Ns + k = exp(-2 pi i k r / (Ns R)), so that
 	 * consecutive butterflies (consecutive k) read consecutive table entries */

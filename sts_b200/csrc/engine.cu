@@ -274,7 +274,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	if (en & (1u << STSGPU_TEST_DFT)) {
 		if (!dft_make_plan(n, &ctx->dft))
 			return fail_create(ctx, STSGPU_E_UNSUPPORTED,
-					   "DFT test: n/2 must split into two 5-smooth factors <= 3200 (powers of two up to 2^23, "
+					   "DFT test: n/2 must split into two 5-smooth factors of at most ~4000 (powers of two up to 2^23, "
 					   "10^6, 10^7 ...); clear bit 7 of test_mask for other stream lengths");
 	}
 

@@ -16,10 +16,10 @@
  *                     X_q = (Z_q + conj Z_{N-q})/2 - (i/2) W_n^q (Z_q - conj Z_{N-q}) and the count
  *                     are finished in shared memory; only N_1 leaves the kernel.
  *
- * Each 1-D FFT is a Stockham autosort FFT out of two shared-memory buffers (ping-pong), one pass per
- * radix of the plan (8, 5, 4, 3 or 2), a thread looping over the butterflies of the pass; twiddles
- * come from per-pass tables computed on the host in long double and laid out so that consecutive
- * butterflies read consecutive entries.
+ * Each 1-D FFT is a Stockham autosort FFT, one pass per radix of the plan (8, 5, 4, 3 or 2), in ONE
+ * shared-memory buffer: a thread keeps its (at most two) butterflies of the pass in registers across
+ * the barrier between reading and writing.  Twiddles come from per-pass tables computed on the host in
+ * long double and laid out so that consecutive butterflies read consecutive entries.
  *
  * Roofline: the intermediate Y is the traffic: 16 N bytes written + 16 N bytes read per stream
  * against n/8 input bytes; FP64 work is about 5 N log2 N flop.
@@ -31,7 +31,6 @@
 
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 
-#define GDFT_THREADS 512
 
 template <> __device__ __forceinline__ void bfly<3>(double2 *v)
 {
@@ -59,93 +58,152 @@ template <> __device__ __forceinline__ void bfly<5>(double2 *v)
 	v[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
 }
 
-__device__ __forceinline__ void bfly_any(double2 *v, int R)
-{
-	switch (R) {
-	case 8: bfly<8>(v); break;
-	case 5: bfly<5>(v); break;
-	case 4: bfly<4>(v); break;
-	case 3: bfly<3>(v); break;
-	default: bfly<2>(v); break;
-	}
-}
-
 /*
- * One Stockham pass of radix R over an FFT of length Nf laid out with element stride `es` (and a
- * fixed offset already folded into src/dst): butterfly b reads src[(b + r Nf/R) es], multiplies by
- * W_(Ns R)^(k r), k = b mod Ns (table of this pass: wtab[(r - 1) Ns + k]), and writes
- * dst[((b - k) R + k + r Ns) es].
+ * A Stockham pass of radix R with the butterflies held in registers: a thread owns up to GDFT_MAXB
+ * butterflies of the pass (work items tid, tid + T, ...), reads their inputs, applies the pass's
+ * twiddles W_(Ns R)^(k r) (table entry (r - 1) Ns + k, k = b mod Ns) and the butterfly, and after a
+ * barrier writes the outputs at ((b - k) R + k + r Ns) of the SAME buffer.  The first pass reads from
+ * global memory (packed bits / the intermediate Y), the last pass of the columns writes Y.
  */
-__device__ __forceinline__ void stockham_butterfly(const double2 *src, double2 *dst, int es, int Nf, int R, int Ns, int b,
-						     const double2 *__restrict__ wtab)
+#define GDFT_MAXB 2
+
+template <int R> __device__ __forceinline__ void tw_bfly(double2 *v, const double2 *__restrict__ wtab, int Ns, int k)
 {
-	double2 v[8];
-	const int q = Nf / R;
-#pragma unroll
-	for (int r = 0; r < 8; r++)
-		if (r < R)
-			v[r] = src[(b + r * q) * es];
-	const int k = b % Ns;
 	if (Ns > 1) {
 #pragma unroll
-		for (int r = 1; r < 8; r++)
-			if (r < R)
-				v[r] = cmul(v[r], __ldg(wtab + (r - 1) * Ns + k));
+		for (int r = 1; r < R; r++)
+			v[r] = cmul(v[r], __ldg(wtab + (r - 1) * Ns + k));
 	}
-	bfly_any(v, R);
-	const int base = (b - k) * R + k;
-#pragma unroll
-	for (int r = 0; r < 8; r++)
-		if (r < R)
-			dst[(base + r * Ns) * es] = v[r];
+	bfly<R>(v);
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(GDFT_THREADS)
-dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
+template <int R>
+__device__ __forceinline__ void cols_pass(const DevParams &P, const DftPlan &D, const uint32_t *__restrict__ w, double2 *buf,
+					  double2 *__restrict__ Ys, int j20, int ps, int Ns)
 {
-	extern __shared__ double2 buf[];			/* [2][N1][CW] */
-	const int N1 = D.N1, N2 = D.N2, CW = D.cw;
-	const int64_t sl = blockIdx.x;				/* stream inside the chunk */
-	const uint32_t *__restrict__ w = in + (stream0 + sl) * P.pitch_words;
-	double2 *__restrict__ Ys = Y + sl * ((int64_t) N1 * N2);
-	const int j20 = blockIdx.y * CW;
-	double2 *a = buf, *b = buf + (size_t) N1 * CW;
-
-	/* z[N2 j1 + j2] = x_2j + i x_2j+1 from the packed bits */
-	for (int e = threadIdx.x; e < N1 * CW; e += GDFT_THREADS) {
-		const int j1 = e / CW, c = e % CW;
-		const int64_t p = 2 * ((int64_t) N2 * j1 + j20 + c);
-		const uint32_t two = (ldw(w, p >> 5) >> (30 - (int) (p & 31))) & 3u;
-		a[e] = make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
+	const int N1 = D.N1, N2 = D.N2, CW = D.cw, T = D.threads;
+	const int q = N1 / R, total = q * CW;
+	const bool first = (ps == 0), last = (ps == D.np1 - 1);
+	double2 v[GDFT_MAXB][R];
+	int kk[GDFT_MAXB];
+#pragma unroll
+	for (int i = 0; i < GDFT_MAXB; i++) {
+		const int it = threadIdx.x + i * T;
+		if (it < total) {
+			const int b = it / CW, c = it - b * CW;
+			if (first) {
+#pragma unroll
+				for (int r = 0; r < R; r++) {	/* z[N2 j1 + j2] = x_2j + i x_2j+1 from the packed bits */
+					const int64_t p = 2 * ((int64_t) N2 * (b + r * q) + j20 + c);
+					const uint32_t two = (ldw(w, p >> 5) >> (30 - (int) (p & 31))) & 3u;
+					v[i][r] = make_double2((two & 2u) ? 1.0 : -1.0, (two & 1u) ? 1.0 : -1.0);
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					v[i][r] = buf[(b + r * q) * CW + c];
+			}
+			kk[i] = b % Ns;
+			tw_bfly<R>(v[i], D.w1 + D.off1[ps], Ns, kk[i]);
+		}
 	}
 	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < GDFT_MAXB; i++) {
+		const int it = threadIdx.x + i * T;
+		if (it < total) {
+			const int b = it / CW, c = it - b * CW;
+			const int base = (b - kk[i]) * R + kk[i];
+			if (last) {		/* times W_N^(j2 k1), out as Y[k1][j2] */
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					const int k1 = base + r * Ns;
+					const int64_t x = (int64_t) (j20 + c) * k1;		/* < N */
+					const double2 tw = cmul(__ldg(D.th + (x >> 10)), __ldg(D.tl + (x & 1023)));
+					Ys[(int64_t) k1 * N2 + j20 + c] = cmul(v[i][r], tw);
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					buf[(base + r * Ns) * CW + c] = v[i][r];
+			}
+		}
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(512, 1)
+dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
+{
+	extern __shared__ double2 buf[];			/* [N1][CW] */
+	const int64_t sl = blockIdx.x;				/* stream inside the chunk */
+	const uint32_t *__restrict__ w = in + (stream0 + sl) * P.pitch_words;
+	double2 *__restrict__ Ys = Y + sl * ((int64_t) D.N1 * D.N2);
+	const int j20 = blockIdx.y * D.cw;
 	int Ns = 1;
 	for (int ps = 0; ps < D.np1; ps++) {
 		const int R = D.rad1[ps];
-		const int nb = N1 / R;
-		for (int e = threadIdx.x; e < nb * CW; e += GDFT_THREADS) {
-			const int bb = e / CW, c = e % CW;
-			stockham_butterfly(a + c, b + c, CW, N1, R, Ns, bb, D.w1 + D.off1[ps]);
+		switch (R) {
+		case 8: cols_pass<8>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 5: cols_pass<5>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 4: cols_pass<4>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 3: cols_pass<3>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		default: cols_pass<2>(P, D, w, buf, Ys, j20, ps, Ns); break;
 		}
-		__syncthreads();
-		double2 *t = a; a = b; b = t;
 		Ns *= R;
-	}
-	/* times W_N^(j2 k1), out as Y[k1][j2] */
-	for (int e = threadIdx.x; e < N1 * CW; e += GDFT_THREADS) {
-		const int k1 = e / CW, c = e % CW;
-		const int64_t x = (int64_t) (j20 + c) * k1;		/* < N */
-		const double2 tw = cmul(__ldg(D.th + (x >> 10)), __ldg(D.tl + (x & 1023)));
-		Ys[(int64_t) k1 * N2 + j20 + c] = cmul(a[e], tw);
 	}
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(GDFT_THREADS)
+template <int R>
+__device__ __forceinline__ void rows_pass(const DftPlan &D, const double2 *__restrict__ Ys, double2 *buf, int k1a, int k1b, int rows,
+					  int ps, int Ns)
+{
+	const int N2 = D.N2, T = D.threads;
+	const int q = N2 / R, total = rows * q;
+	const bool first = (ps == 0);
+	double2 v[GDFT_MAXB][R];
+	int kk[GDFT_MAXB];
+#pragma unroll
+	for (int i = 0; i < GDFT_MAXB; i++) {
+		const int it = threadIdx.x + i * T;
+		if (it < total) {
+			const int r_ = it / q, b = it - r_ * q;
+			if (first) {
+				const double2 *__restrict__ src = Ys + (int64_t) (r_ ? k1b : k1a) * N2;
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					v[i][r] = src[b + r * q];
+			} else {
+				const double2 *src = buf + (size_t) r_ * N2;
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					v[i][r] = src[b + r * q];
+			}
+			kk[i] = b % Ns;
+			tw_bfly<R>(v[i], D.w2 + D.off2[ps], Ns, kk[i]);
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < GDFT_MAXB; i++) {
+		const int it = threadIdx.x + i * T;
+		if (it < total) {
+			const int r_ = it / q, b = it - r_ * q;
+			double2 *dst = buf + (size_t) r_ * N2 + (b - kk[i]) * R + kk[i];
+#pragma unroll
+			for (int r = 0; r < R; r++)
+				dst[r * Ns] = v[i][r];
+		}
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(512, 1)
 dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
-	extern __shared__ double2 buf[];			/* [2 rows][2][N2] */
+	extern __shared__ double2 buf[];			/* [2 rows][N2] */
 	__shared__ unsigned int cnt_s;
 	const int N1 = D.N1, N2 = D.N2;
 	const int64_t sl = blockIdx.x;
@@ -155,31 +213,26 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 	const int rows = self ? 1 : 2;
 	if (threadIdx.x == 0)
 		cnt_s = 0;
-	for (int e = threadIdx.x; e < rows * N2; e += GDFT_THREADS) {
-		const int r_ = e / N2, j2 = e % N2;
-		buf[(size_t) r_ * 2 * N2 + j2] = Ys[(int64_t) (r_ ? k1b : k1a) * N2 + j2];
-	}
-	__syncthreads();
-	int Ns = 1, cur = 0;
+	int Ns = 1;
 	for (int ps = 0; ps < D.np2; ps++) {
 		const int R = D.rad2[ps];
-		const int nb = N2 / R;
-		for (int e = threadIdx.x; e < rows * nb; e += GDFT_THREADS) {
-			const int r_ = e / nb, bb = e % nb;
-			double2 *base = buf + (size_t) r_ * 2 * N2;
-			stockham_butterfly(base + cur * N2, base + (cur ^ 1) * N2, 1, N2, R, Ns, bb, D.w2 + D.off2[ps]);
+		switch (R) {
+		case 8: rows_pass<8>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 5: rows_pass<5>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 4: rows_pass<4>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 3: rows_pass<3>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		default: rows_pass<2>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
 		}
-		__syncthreads();
-		cur ^= 1;
 		Ns *= R;
 	}
 	/* real-FFT post pass + count, discreteFourierTransform.c:392-411 (bins 0 .. n/2 - 1 = all q < N) */
+	const double T2x4 = 4.0 * D.T * D.T;			/* |X| < T  <=>  |2X|^2 < 4 T^2 (see k_dft_fast.cu) */
 	unsigned int cnt = 0;
-	for (int e = threadIdx.x; e < rows * N2; e += GDFT_THREADS) {
-		const int r_ = e / N2, k2 = e % N2;
+	for (int e = threadIdx.x; e < rows * N2; e += D.threads) {
+		const int r_ = e / N2, k2 = e - r_ * N2;
 		const int kq = r_ ? k1b : k1a;			/* q = kq + N1 k2 */
-		const double2 *mine = buf + ((size_t) r_ * 2 + cur) * N2;
-		const double2 *other = buf + ((size_t) (self ? 0 : (1 - r_)) * 2 + cur) * N2;
+		const double2 *mine = buf + (size_t) r_ * N2;
+		const double2 *other = buf + (size_t) (self ? 0 : (1 - r_)) * N2;
 		const int k2p = (kq == 0) ? ((N2 - k2) % N2) : (N2 - 1 - k2);
 		const double2 zq = mine[k2];
 		double2 zp = other[k2p];
@@ -187,10 +240,9 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 		const double2 wq = cmul(__ldg(D.p1 + kq), __ldg(D.p2 + k2));	/* exp(-2 pi i q / n) */
 		const double2 sum = cadd(zq, zp), dif = csub(zq, zp);
 		const double2 wd = cmul(wq, dif);
-		/* X = sum/2 - (i/2) wd  =  (sum.x + wd.y, sum.y - wd.x) / 2 */
-		const double xr = 0.5 * (sum.x + wd.y), xi = 0.5 * (sum.y - wd.x);
-		const double mod = sqrt(xr * xr + xi * xi);
-		cnt += (mod < D.T) ? 1u : 0u;
+		/* 2 X = sum - i wd = (sum.x + wd.y, sum.y - wd.x) */
+		const double xr = sum.x + wd.y, xi = sum.y - wd.x;
+		cnt += (xr * xr + xi * xi < T2x4) ? 1u : 0u;
 	}
 	cnt = (unsigned int) warp_sum((int) cnt);
 	if ((threadIdx.x & 31) == 0 && cnt)
@@ -223,33 +275,51 @@ bool dft_make_plan(long long n, DftPlan *D)
 	if (n < 16 || (n & 1))
 		return false;
 	const long long N = n / 2;
-	const long long LIM = 3200;		/* rows: 2 rows x 2 buffers x N2 x 16 B <= 200 KiB */
+	/*
+	 * Every pass keeps its butterflies in registers, at most GDFT_MAXB per thread: with T threads,
+	 * rows: 2 N2 / R <= MAXB T, columns: CW N1 / R <= MAXB T for every radix R of the list.  Among the
+	 * feasible splits take the widest column tile (coalesced Y stores), then 256 threads (two CTAs per
+	 * SM), then the longest rows.
+	 */
+	int best_cw = 0, best_t = 0;
 	long long best1 = 0, best2 = 0;
-	for (long long n2 = 2; n2 <= LIM && n2 <= N; n2++) {
-		if (N % n2)
-			continue;
-		const long long n1 = N / n2;
-		if (n1 > LIM || n1 < 2)
-			continue;
-		int r[DFT_MAX_PASSES], k;
-		if (!radix_list((int) n1, r, &k) || !radix_list((int) n2, r, &k))
-			continue;
-		/* the most balanced split (fewest passes over the longest FFT), N2 >= N1 */
-		if (n2 >= n1 && (best2 == 0 || n2 - n1 < best2 - best1)) {
-			best1 = n1;
-			best2 = n2;
+	for (int T = 256; T <= 512; T *= 2) {
+		for (long long n2 = 2; n2 <= 4096 && n2 <= N; n2++) {
+			if (N % n2)
+				continue;
+			const long long n1 = N / n2;
+			if (n1 > 4096 || n1 < 2)
+				continue;
+			int r1[DFT_MAX_PASSES], r2[DFT_MAX_PASSES], k1, k2;
+			if (!radix_list((int) n1, r1, &k1) || !radix_list((int) n2, r2, &k2))
+				continue;
+			int min1 = 8, min2 = 8;
+			for (int i = 0; i < k1; i++) min1 = r1[i] < min1 ? r1[i] : min1;
+			for (int i = 0; i < k2; i++) min2 = r2[i] < min2 ? r2[i] : min2;
+			if (2 * (n2 / min2) > (long long) GDFT_MAXB * T)
+				continue;
+			if ((size_t) 2 * n2 * sizeof(double2) > 200 * 1024)
+				continue;
+			int cw = 16;
+			while (cw >= 1 && (n2 % cw != 0 || (long long) cw * (n1 / min1) > (long long) GDFT_MAXB * T ||
+					   (size_t) n1 * cw * sizeof(double2) > 200 * 1024))
+				cw >>= 1;
+			if (cw < 1)
+				continue;
+			const bool better = cw > best_cw || (cw == best_cw && (T < best_t || (T == best_t && n2 > best2)));
+			if (best_t == 0 || better) {
+				best_cw = cw; best_t = T; best1 = n1; best2 = n2;
+			}
 		}
 	}
-	if (best2 == 0)
+	if (best_t == 0)
 		return false;
 	D->N1 = (int) best1;
 	D->N2 = (int) best2;
+	D->cw = best_cw;
+	D->threads = best_t;
 	radix_list(D->N1, D->rad1, &D->np1);
 	radix_list(D->N2, D->rad2, &D->np2);
-	int cw = 8;
-	while (cw > 1 && (D->N2 % cw != 0 || (size_t) 2 * D->N1 * cw * sizeof(double2) > 200 * 1024))
-		cw >>= 1;
-	D->cw = cw;
 	return true;
 }
 
@@ -259,8 +329,8 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 		return cudaSuccess;
 	if (D.fast)
 		return launch_dft_fast(P, L, D, d_work, work_streams);
-	const size_t smem1 = (size_t) 2 * D.N1 * D.cw * sizeof(double2);
-	const size_t smem2 = (size_t) 4 * D.N2 * sizeof(double2);
+	const size_t smem1 = (size_t) D.N1 * D.cw * sizeof(double2);
+	const size_t smem2 = (size_t) 2 * D.N2 * sizeof(double2);
 	cudaError_t e;
 	e = cudaFuncSetAttribute(dft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
 	if (e != cudaSuccess) return e;
@@ -269,9 +339,9 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams) {
 		const int64_t cs = (L.nstreams - s0 < work_streams) ? L.nstreams - s0 : work_streams;
 		dim3 g1((unsigned) cs, (unsigned) (D.N2 / D.cw));
-		dft_cols_kernel<<<g1, GDFT_THREADS, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		dft_cols_kernel<<<g1, D.threads, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
 		dim3 g2((unsigned) cs, (unsigned) (D.N1 / 2 + 1));
-		dft_rows_kernel<<<g2, GDFT_THREADS, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		dft_rows_kernel<<<g2, D.threads, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
 	}
 	return cudaGetLastError();
 }
