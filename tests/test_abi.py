@@ -62,9 +62,9 @@ def test_product_never_imports_the_oracle():
 
 
 def test_dft_supported_lengths():
-    """host-side FFT planning (no CUDA call): n/2 must split into two 5-smooth factors <= 3200"""
+    """host-side FFT planning (no CUDA call): n/2 must split into two 5-smooth factors that fit the register-resident passes"""
     import sts_b200 as sts
-    for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
+    for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 1 << 25, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
         assert sts.dft_supported(n), n
-    for n in (1000008, 2 * 1000003, 14 * (1 << 16), 1 << 25):
+    for n in (1000008, 2 * 1000003, 14 * (1 << 16), 1 << 27):
         assert not sts.dft_supported(n), n

@@ -274,6 +274,8 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     (7, dict(n=1 << 14)),                                # DFT: generic path, small power of two
     (7, dict(n=5 * (1 << 16))),                          # DFT: one radix-5 pass
     (7, dict(n=1 << 22)),                                # DFT: generic path above the fast kernel's length
+    (7, dict(n=1 << 25)),                                # DFT: 4096 x 4096, the largest split
+    (7, dict(n=3 * 5 * (1 << 15))),                      # DFT: radices 3 and 5 together
 ])
 def test_single_test_parameter_sweep(sts, oracle, test, prm):
     """kernel variants the default parameters never reach, one test at a time, bit-exact / 1e-9 against the oracle"""
