@@ -11,7 +11,7 @@ struct DftPlan {
 	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
 	int threads;		/* CTA size of the generic kernels (256 or 512) */
-	int fast;		/* n = 2^20: the specialised kernels of k_dft_fast.cu */
+	int fast;		/* 1: n = 2^20, the kernels of k_dft_fast.cu; 2: n = 10^6, k_dft_1e6.cu; 0: generic */
 	/* per-pass twiddles, pass p at offset off[p]: entry (r - 1) Ns + k = exp(-2 pi i k r / (Ns R)), so that
 	 * consecutive butterflies (consecutive k) read consecutive table entries */
 	const double2 *w1;
@@ -28,6 +28,15 @@ struct DftPlan {
 	const double2 *q_e2;	/* [2048]: exp(-2 pi i 16 j2 / N) */
 	const double2 *q_p1;	/* [256]:  exp(-2 pi i k1 / n) */
 	const double2 *q_p2;	/* [2048]: exp(-2 pi i 256 k2 / n) */
+	/* tables of the n = 10^6 kernels (k_dft_1e6.cu, N = 500 x 1000), NULL otherwise */
+	const double2 *m_twA;	/* [9][5]:    exp(-2 pi i k r / 50),   r = 1..9, k < 5   (column pass, Ns = 5) */
+	const double2 *m_twB;	/* [9][50]:   exp(-2 pi i k r / 500),  k < 50            (column pass, Ns = 50) */
+	const double2 *m_twC;	/* [9][10]:   exp(-2 pi i k r / 100),  k < 10            (row pass, Ns = 10) */
+	const double2 *m_twD;	/* [9][100]:  exp(-2 pi i k r / 1000), k < 100           (row pass, Ns = 100) */
+	const double2 *m_e1;	/* [50][1000]: exp(-2 pi i j2 t / N) */
+	const double2 *m_e2;	/* [1000]: exp(-2 pi i 50 j2 / N) */
+	const double2 *m_p1;	/* [500]:  exp(-2 pi i k1 / n) */
+	const double2 *m_p2;	/* [1000]: exp(-2 pi i 500 k2 / n) */
 	double T;		/* sqrt(log(20) * n), discreteFourierTransform.c:142 */
 };
 

@@ -51,3 +51,58 @@ template <> __device__ __forceinline__ void bfly<8>(double2 *v)
 /* padded shared-memory index: one spare element per 8 keeps radix-8 scatter stores conflict free */
 __device__ __forceinline__ int padi(int e) { return e + (e >> 3); }
 
+template <> __device__ __forceinline__ void bfly<3>(double2 *v)
+{
+	const double s = 0.86602540378443864676;
+	const double2 a = cadd(v[1], v[2]), b = csub(v[1], v[2]);
+	const double2 m = make_double2(v[0].x - 0.5 * a.x, v[0].y - 0.5 * a.y);
+	const double2 n = make_double2(s * b.y, -s * b.x);		/* -i s b */
+	v[0] = cadd(v[0], a);
+	v[1] = cadd(m, n);
+	v[2] = csub(m, n);
+}
+template <> __device__ __forceinline__ void bfly<5>(double2 *v)
+{
+	const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+	const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+	const double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+	const double2 m1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+	const double2 m2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+	const double2 n1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+	const double2 n2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+	v[0] = cadd(v[0], cadd(a1, a2));
+	v[1] = make_double2(m1.x + n1.y, m1.y - n1.x);		/* m1 - i n1 */
+	v[4] = make_double2(m1.x - n1.y, m1.y + n1.x);
+	v[2] = make_double2(m2.x + n2.y, m2.y - n2.x);
+	v[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
+}
+
+/* 10-point DFT in registers, natural order in and out: j = j0 + 2 j1, k = k1 + 5 k0 */
+__device__ __forceinline__ void bfly10(double2 *v)
+{
+	double2 a0[5] = { v[0], v[2], v[4], v[6], v[8] }, a1[5] = { v[1], v[3], v[5], v[7], v[9] };
+	bfly<5>(a0);
+	bfly<5>(a1);
+	a1[1] = cmul(a1[1], make_double2(0.80901699437494742410, -0.58778525229247312917));	/* W_10^1 */
+	a1[2] = cmul(a1[2], make_double2(0.30901699437494742410, -0.95105651629515357212));	/* W_10^2 */
+	a1[3] = cmul(a1[3], make_double2(-0.30901699437494742410, -0.95105651629515357212));	/* W_10^3 */
+	a1[4] = cmul(a1[4], make_double2(-0.80901699437494742410, -0.58778525229247312917));	/* W_10^4 */
+#pragma unroll
+	for (int k1 = 0; k1 < 5; k1++) {
+		v[k1] = cadd(a0[k1], a1[k1]);
+		v[k1 + 5] = csub(a0[k1], a1[k1]);
+	}
+}
+
+/* X_q and X_{N-q} from Z_q = zq and Z_{N-q} = zp; wq = exp(-2 pi i q / n); returns how many of the two lie below T */
+__device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double2 wq, double T2x4, bool both)
+{
+	const double2 sum = make_double2(zq.x + zp.x, zq.y - zp.y);	/* Z_q + conj Z_{N-q} */
+	const double2 dif = make_double2(zq.x - zp.x, zq.y + zp.y);	/* Z_q - conj Z_{N-q} */
+	const double2 wd = cmul(wq, dif);
+	const double ar = sum.x + wd.y, ai = sum.y - wd.x;		/* 2 X_q */
+	const double br = sum.x - wd.y, bi = sum.y + wd.x;		/* 2 conj X_{N-q} */
+	/* |X| < T  <=>  |2X|^2 < 4 T^2 up to one rounding, far inside the 1e-9 band the north star allows */
+	const bool below_a = (ar * ar + ai * ai) < T2x4, below_b = (br * br + bi * bi) < T2x4;
+	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
+}

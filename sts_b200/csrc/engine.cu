@@ -424,7 +424,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		DftPlan &D = ctx->dft;				/* N1, N2, radix lists: dft_make_plan above */
 		const int N1 = D.N1, N2 = D.N2;
 		const int64_t N = (int64_t) N1 * N2;
-		D.fast = (n == (1LL << 20)) ? 1 : 0;
+		D.fast = (n == (1LL << 20)) ? 1 : (n == 1000000 ? 2 : 0);
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
 		std::vector<double2> w1(N1), w2(N2), tl(1024), th((size_t) (N / 1024 + 1)), p1(N1), p2(N2);
 		{	/* per-pass twiddle tables (dft.h): entry (r - 1) Ns + k of pass p = exp(-2 pi i k r / (Ns R)) */
@@ -459,7 +459,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		CKC(upload(&d, p1.data(), p1.size()), "upload(fft p1)"); D.p1 = d; ctx->dft_tabs[3] = d;
 		CKC(upload(&d, p2.data(), p2.size()), "upload(fft p2)"); D.p2 = d; ctx->dft_tabs[4] = d;
 		D.q_twA = D.q_twB = D.q_e1 = D.q_e2 = D.q_p1 = D.q_p2 = nullptr;
-		if (D.fast) {							/* n = 2^20: k_dft_fast.cu (its own 256 x 2048 split) */
+		if (D.fast == 1) {						/* n = 2^20: k_dft_fast.cu (its own 256 x 2048 split) */
 			std::vector<double2> tA(15 * 16), tB(7 * 256), e1(16 * 2048), e2(2048), q1(256), q2(2048);
 			for (int r = 1; r < 16; r++)
 				for (int k = 0; k < 16; k++) tA[(r - 1) * 16 + k] = unit_root(k * r, 256);
@@ -476,6 +476,30 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			CKC(upload(&d, e2.data(), e2.size()), "upload(fft e2)"); D.q_e2 = d; ctx->dft_tabs[8] = d;
 			CKC(upload(&d, q1.data(), q1.size()), "upload(fft q1)"); D.q_p1 = d; ctx->dft_tabs[9] = d;
 			CKC(upload(&d, q2.data(), q2.size()), "upload(fft q2)"); D.q_p2 = d; ctx->dft_tabs[10] = d;
+		}
+		D.m_twA = D.m_twB = D.m_twC = D.m_twD = D.m_e1 = D.m_e2 = D.m_p1 = D.m_p2 = nullptr;
+		if (D.fast == 2) {						/* n = 10^6: k_dft_1e6.cu (500 x 1000), one allocation */
+			std::vector<double2> m;
+			size_t o[8];
+			o[0] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 5; k++) m.push_back(unit_root(k * r, 50));
+			o[1] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 50; k++) m.push_back(unit_root(k * r, 500));
+			o[2] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 10; k++) m.push_back(unit_root(k * r, 100));
+			o[3] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 100; k++) m.push_back(unit_root(k * r, 1000));
+			o[4] = m.size();
+			for (int t = 0; t < 50; t++) for (int j2 = 0; j2 < 1000; j2++) m.push_back(unit_root((long double) j2 * t, (long double) N));
+			o[5] = m.size();
+			for (int j2 = 0; j2 < 1000; j2++) m.push_back(unit_root((long double) 50 * j2, (long double) N));
+			o[6] = m.size();
+			for (int k = 0; k < 500; k++) m.push_back(unit_root(k, (long double) n));
+			o[7] = m.size();
+			for (int k = 0; k < 1000; k++) m.push_back(unit_root((long double) 500 * k, (long double) n));
+			CKC(upload(&d, m.data(), m.size()), "upload(fft 1e6 tables)"); ctx->dft_tabs[5] = d;
+			D.m_twA = d + o[0]; D.m_twB = d + o[1]; D.m_twC = d + o[2]; D.m_twD = d + o[3];
+			D.m_e1 = d + o[4]; D.m_e2 = d + o[5]; D.m_p1 = d + o[6]; D.m_p2 = d + o[7];
 		}
 		int64_t chunk = 128;
 		const char *envc = getenv("STSGPU_DFT_CHUNK");

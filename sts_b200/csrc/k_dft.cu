@@ -30,33 +30,8 @@
 #include "dft_math.cuh"
 
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
+cudaError_t launch_dft_1e6(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 
-
-template <> __device__ __forceinline__ void bfly<3>(double2 *v)
-{
-	const double s = 0.86602540378443864676;
-	const double2 a = cadd(v[1], v[2]), b = csub(v[1], v[2]);
-	const double2 m = make_double2(v[0].x - 0.5 * a.x, v[0].y - 0.5 * a.y);
-	const double2 n = make_double2(s * b.y, -s * b.x);		/* -i s b */
-	v[0] = cadd(v[0], a);
-	v[1] = cadd(m, n);
-	v[2] = csub(m, n);
-}
-template <> __device__ __forceinline__ void bfly<5>(double2 *v)
-{
-	const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
-	const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
-	const double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
-	const double2 m1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
-	const double2 m2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
-	const double2 n1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-	const double2 n2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-	v[0] = cadd(v[0], cadd(a1, a2));
-	v[1] = make_double2(m1.x + n1.y, m1.y - n1.x);		/* m1 - i n1 */
-	v[4] = make_double2(m1.x - n1.y, m1.y + n1.x);
-	v[2] = make_double2(m2.x + n2.y, m2.y - n2.x);
-	v[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
-}
 
 /*
  * A Stockham pass of radix R with the butterflies held in registers: a thread owns up to GDFT_MAXB
@@ -327,8 +302,10 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_DFT)))
 		return cudaSuccess;
-	if (D.fast)
+	if (D.fast == 1)
 		return launch_dft_fast(P, L, D, d_work, work_streams);
+	if (D.fast == 2)
+		return launch_dft_1e6(P, L, D, d_work, work_streams);
 	const size_t smem1 = (size_t) D.N1 * D.cw * sizeof(double2);
 	const size_t smem2 = (size_t) 2 * D.N2 * sizeof(double2);
 	cudaError_t e;

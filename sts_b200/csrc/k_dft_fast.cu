@@ -155,19 +155,6 @@ dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__r
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* X_q and X_{N-q} from Z_q = zq and Z_{N-q} = zp; wq = exp(-2 pi i q / n); returns how many of the two lie below T */
-__device__ __forceinline__ unsigned int post_pair(double2 zq, double2 zp, double2 wq, double T2x4, bool both)
-{
-	const double2 sum = make_double2(zq.x + zp.x, zq.y - zp.y);	/* Z_q + conj Z_{N-q} */
-	const double2 dif = make_double2(zq.x - zp.x, zq.y + zp.y);	/* Z_q - conj Z_{N-q} */
-	const double2 wd = cmul(wq, dif);
-	const double ar = sum.x + wd.y, ai = sum.y - wd.x;		/* 2 X_q */
-	const double br = sum.x - wd.y, bi = sum.y + wd.x;		/* 2 conj X_{N-q} */
-	/* |X| < T  <=>  |2X|^2 < 4 T^2 up to one rounding, far inside the 1e-9 band the north star allows */
-	const bool below_a = (ar * ar + ai * ai) < T2x4, below_b = (br * br + bi * bi) < T2x4;
-	return (below_a ? 1u : 0u) + ((both && below_b) ? 1u : 0u);
-}
-
 __global__ void DFT_BOUNDS
 dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
