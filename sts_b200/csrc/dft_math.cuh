@@ -77,21 +77,18 @@ template <> __device__ __forceinline__ void bfly<5>(double2 *v)
 	v[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
 }
 
-/* 10-point DFT in registers, natural order in and out: j = j0 + 2 j1, k = k1 + 5 k0 */
+/* 10-point DFT in registers, natural order in and out.  10 = 2 x 5 with coprime factors, so the prime-factor
+ * index maps j = (5 j1 + 2 j2) mod 10, k = (5 k1 + 6 k2) mod 10 leave no twiddles between the two stages */
 __device__ __forceinline__ void bfly10(double2 *v)
 {
-	double2 a0[5] = { v[0], v[2], v[4], v[6], v[8] }, a1[5] = { v[1], v[3], v[5], v[7], v[9] };
+	double2 a0[5] = { v[0], v[2], v[4], v[6], v[8] }, a1[5] = { v[5], v[7], v[9], v[1], v[3] };
 	bfly<5>(a0);
 	bfly<5>(a1);
-	a1[1] = cmul(a1[1], make_double2(0.80901699437494742410, -0.58778525229247312917));	/* W_10^1 */
-	a1[2] = cmul(a1[2], make_double2(0.30901699437494742410, -0.95105651629515357212));	/* W_10^2 */
-	a1[3] = cmul(a1[3], make_double2(-0.30901699437494742410, -0.95105651629515357212));	/* W_10^3 */
-	a1[4] = cmul(a1[4], make_double2(-0.80901699437494742410, -0.58778525229247312917));	/* W_10^4 */
-#pragma unroll
-	for (int k1 = 0; k1 < 5; k1++) {
-		v[k1] = cadd(a0[k1], a1[k1]);
-		v[k1 + 5] = csub(a0[k1], a1[k1]);
-	}
+	v[0] = cadd(a0[0], a1[0]); v[5] = csub(a0[0], a1[0]);
+	v[6] = cadd(a0[1], a1[1]); v[1] = csub(a0[1], a1[1]);
+	v[2] = cadd(a0[2], a1[2]); v[7] = csub(a0[2], a1[2]);
+	v[8] = cadd(a0[3], a1[3]); v[3] = csub(a0[3], a1[3]);
+	v[4] = cadd(a0[4], a1[4]); v[9] = csub(a0[4], a1[4]);
 }
 
 /* X_q and X_{N-q} from Z_q = zq and Z_{N-q} = zp; wq = exp(-2 pi i q / n); returns how many of the two lie below T */

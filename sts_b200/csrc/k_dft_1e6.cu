@@ -108,7 +108,7 @@ dft_cols_1e6(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *_
 
 /* ------------------------------------------------------------------------------------------ */
 #ifndef M_ROWS_MINCTA
-#define M_ROWS_MINCTA 2
+#define M_ROWS_MINCTA 3		/* measured: 2 CTAs (122 regs) 6.58 ms, 3 (80) 6.31, 4 (72) 6.82 per 1024 streams */
 #endif
 __global__ void __launch_bounds__(200, M_ROWS_MINCTA)
 dft_rows_1e6(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
