@@ -175,6 +175,26 @@ int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams, int64_t
  */
 int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration);
 
+/*
+ * "-F a" input (replaces parseBitsASCIIInput, utilities.c:1651-1727): `text` holds `text_len` characters of the
+ * data file starting at the character offset of the batch's first stream (base_seek + first_iteration * n,
+ * utilities.c:1511 and :1682-1683), borrowed until stsgpu_wait returns.  Stream k of the batch is the first n
+ * characters '0' / '1' at or after text[k * n], white space skipped - the reference seeks to that offset for
+ * every iteration, so in a file with line breaks consecutive streams overlap exactly as they do there.  Pass up
+ * to (nstreams + 1) * n characters: the extra stream's worth is the room for white space.  The digits are packed
+ * on the device; otherwise as stsgpu_submit.  After stsgpu_wait, stsgpu_results reports only the leading
+ * streams that were complete, and stsgpu_ascii_status tells why the rest are missing.
+ */
+int stsgpu_submit_ascii(stsgpu_ctx *ctx, const char *text, int64_t text_len, int64_t nstreams, int64_t first_iteration);
+
+/*
+ * For the batch stsgpu_wait last completed, if it was an ASCII batch: *complete_streams = number of leading
+ * streams that found their n digits inside `text` (the reference warns "Insufficient data" for the first
+ * incomplete one, utilities.c:1693-1697); *bad_offset = offset in `text` of the first character that is neither
+ * 0, 1 nor white space among those the reference would have scanned, or -1.
+ */
+int stsgpu_ascii_status(stsgpu_ctx *ctx, int64_t *complete_streams, int64_t *bad_offset);
+
 /* copy raw bytes into the device input buffer without running the tests */
 int stsgpu_upload(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstreams);
 

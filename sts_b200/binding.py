@@ -19,7 +19,7 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
 EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_dft_supported", "stsgpu_submit",
-           "stsgpu_submit_resident", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
+           "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
            "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
@@ -83,6 +83,8 @@ def load_library():
     lib.stsgpu_dft_supported.argtypes = [i64]
     lib.stsgpu_submit.argtypes = [vp, vp, i64, i64]
     lib.stsgpu_submit_resident.argtypes = [vp, i64, i64]
+    lib.stsgpu_submit_ascii.argtypes = [vp, vp, i64, i64, i64]
+    lib.stsgpu_ascii_status.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.stsgpu_upload.argtypes = [vp, vp, i64]
     lib.stsgpu_wait.argtypes = [vp]
     lib.stsgpu_pending.argtypes = [vp]
@@ -195,6 +197,17 @@ class Engine:
         else:
             ptr = raw
         self._ck(self.lib.stsgpu_submit(self.h, ptr, nstreams, first_iteration), "submit")
+
+    def submit_ascii(self, text, nstreams, first_iteration=0):
+        """text: bytes-like / uint8 array of '0' / '1' characters and white space, starting at the batch's first stream"""
+        text = np.ascontiguousarray(np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text)
+        self._keep = (getattr(self, "_keep", ()) + (text,))[-4:]
+        self._ck(self.lib.stsgpu_submit_ascii(self.h, text.ctypes.data, text.size, nstreams, first_iteration), "submit_ascii")
+
+    def ascii_status(self):
+        done, bad = C.c_int64(), C.c_int64()
+        self._ck(self.lib.stsgpu_ascii_status(self.h, C.byref(done), C.byref(bad)), "ascii_status")
+        return done.value, bad.value
 
     def submit_resident(self, nstreams, first_iteration=0):
         self._ck(self.lib.stsgpu_submit_resident(self.h, nstreams, first_iteration), "submit_resident")

@@ -530,6 +530,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		cudaFree(S.d_in); cudaFree(S.d_pv); cudaFree(S.d_st); cudaFree(S.d_w);
 		cudaFreeHost(S.h_pv); cudaFreeHost(S.h_st); cudaFreeHost(S.h_w);
 		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags);
+		cudaFree(S.d_text); cudaFree(S.d_ascii); cudaFreeHost(S.h_ascii);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
 		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
 		if (S.s_uni) cudaStreamDestroy(S.s_uni);
@@ -684,7 +685,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		S.nkernels++;
 	}
 	if (ctx->assessing) {		/* add this batch's p-values to the assessment tallies */
-		cudaError_t e = launch_assess_tally(P, L, ctx->assess_bins, ctx->assess_alpha, ctx->d_tally);
+		cudaError_t e = launch_assess_tally(P, L, ctx->assess_bins, ctx->assess_alpha, ctx->d_tally, S.ascii ? S.d_ascii : nullptr);
 		if (e != cudaSuccess) {
 			set_err(ctx, "assess tally", e);
 			return STSGPU_E_CUDA;
@@ -697,6 +698,8 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	CK(cudaMemcpyAsync(S.h_st, S.d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sl));
 	if (lay.nw)
 		CK(cudaMemcpyAsync(S.h_w, S.d_w, (size_t) nstreams * lay.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl));
+	if (S.ascii)
+		CK(cudaMemcpyAsync(S.h_ascii, S.d_ascii, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl));
 	CK(cudaEventRecord(S.ev_done, sl));
 	S.nstreams = nstreams;
 	S.first = first_iteration;
@@ -742,7 +745,9 @@ extern "C" int stsgpu_submit(stsgpu_ctx *ctx, const uint8_t *raw, int64_t nstrea
 {
 	int rc = stsgpu_upload(ctx, raw, nstreams);
 	if (rc) return rc;
-	return run_tests(ctx, ctx->slots[ctx->submit_seq % ctx->nslots], nstreams, first_iteration);
+	Slot &S = ctx->slots[ctx->submit_seq % ctx->nslots];
+	S.ascii = false;
+	return run_tests(ctx, S, nstreams, first_iteration);
 }
 
 extern "C" int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t first_iteration)
@@ -750,7 +755,62 @@ extern "C" int stsgpu_submit_resident(stsgpu_ctx *ctx, int64_t nstreams, int64_t
 	Slot *S;
 	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
+	S->ascii = false;
 	return run_tests(ctx, *S, nstreams, first_iteration);
+}
+
+/*
+ * "-F a": stream k of the batch is the first n digits at or after text[k n] (the reference's seek rule,
+ * utilities.c:1682-1683), packed on the device by k_ascii.cu.  The staging buffer is allocated on first use.
+ */
+extern "C" int stsgpu_submit_ascii(stsgpu_ctx *ctx, const char *text, int64_t text_len, int64_t nstreams, int64_t first_iteration)
+{
+	Slot *Sp;
+	int rc = next_slot(ctx, nstreams, &Sp);
+	if (rc) return rc;
+	Slot &S = *Sp;
+	if (text == NULL || text_len < 0) return STSGPU_E_INVAL;
+	const int64_t n = ctx->P.n;
+	const int64_t cap = (ctx->prm.max_streams + 1) * n;		/* one stream of slack for white space */
+	if (text_len > cap)
+		text_len = cap;
+	if (S.d_text == nullptr) {
+		if (cudaMalloc((void **) &S.d_text, (size_t) cap + 16) != cudaSuccess ||
+		    cudaMalloc((void **) &S.d_ascii, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+		    cudaMallocHost((void **) &S.h_ascii, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+			snprintf(ctx->err, sizeof(ctx->err), "cannot allocate the %lld-byte ASCII staging buffer", (long long) cap);
+			return STSGPU_E_NOMEM;
+		}
+		S.text_cap = (size_t) cap;
+	}
+	CK(cudaMemcpyAsync(S.d_text, text, (size_t) text_len, cudaMemcpyHostToDevice, S.s_light));
+	CK(cudaMemsetAsync(S.d_ascii, 0xFF, 2 * sizeof(unsigned long long), S.s_light));
+	cudaError_t e = launch_ascii_pack(ctx->P, S.d_text, text_len, S.d_in, S.d_ascii, nstreams, S.s_light);
+	if (e != cudaSuccess) {
+		set_err(ctx, "ascii pack", e);
+		return STSGPU_E_CUDA;
+	}
+	ctx->launches += 1;
+	S.ascii = true;
+	return run_tests(ctx, S, nstreams, first_iteration);
+}
+
+extern "C" int stsgpu_ascii_status(stsgpu_ctx *ctx, int64_t *complete_streams, int64_t *bad_offset)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->have_results) {
+		snprintf(ctx->err, sizeof(ctx->err), "no completed batch");
+		return STSGPU_E_STATE;
+	}
+	const Slot &S = ctx->slots[ctx->last_done];
+	if (!S.ascii) {
+		snprintf(ctx->err, sizeof(ctx->err), "the last completed batch was not submitted with stsgpu_submit_ascii");
+		return STSGPU_E_STATE;
+	}
+	if (complete_streams) *complete_streams = S.nstreams;
+	if (bad_offset) *bad_offset = (S.h_ascii[1] == ~0ull) ? -1 : (int64_t) S.h_ascii[1];
+	return STSGPU_OK;
 }
 
 extern "C" int stsgpu_wait(stsgpu_ctx *ctx)
@@ -768,6 +828,8 @@ extern "C" int stsgpu_wait(stsgpu_ctx *ctx)
 	ctx->wait_seq++;
 	CK(cudaEventSynchronize(S.ev_done));
 	CK(cudaGetLastError());
+	if (S.ascii && S.h_ascii[0] < (unsigned long long) S.nstreams)
+		S.nstreams = (int64_t) S.h_ascii[0];		/* the text ended inside stream h_ascii[0] */
 	ctx->last_done = idx;
 	ctx->d_pv = S.d_pv;
 	ctx->h_pv = S.h_pv;

@@ -27,6 +27,11 @@ struct Slot {
 	uint32_t *d_apen_hist = nullptr;
 	uint32_t *d_hist_flags = nullptr;	/* streams the packed 16-bit histogram could not count exactly */
 	double2 *d_dft_work = nullptr;
+	/* "-F a" batches (k_ascii.cu): text staging, {first incomplete stream, first bad character} */
+	unsigned char *d_text = nullptr;
+	size_t text_cap = 0;
+	unsigned long long *d_ascii = nullptr, *h_ascii = nullptr;
+	bool ascii = false;
 	cudaStream_t s_light = nullptr, s_uni = nullptr, s_heavy = nullptr, s_dft[2] = { nullptr, nullptr };
 	cudaEvent_t ev_join_uni = nullptr, ev_join_dft = nullptr;
 	cudaEvent_t ev_dft_fork = nullptr, ev_dft_join = nullptr;
@@ -91,7 +96,8 @@ void stsgpu_comm_destroy_internal(stsgpu_ctx *ctx);
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
 			 cudaStream_t s_cusum, cudaStream_t s_apen);
 cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
-cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally);
+cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally,
+				const unsigned long long *d_limit);
 cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha, double level, double lgam, const unsigned long long *d_tally,
 				 stsgpu_metric *d_out, cudaStream_t stream);
 cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);

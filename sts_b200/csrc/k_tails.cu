@@ -410,11 +410,13 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
  */
 __global__ void __launch_bounds__(256)
 assess_tally_kernel(DevParams P, const double *__restrict__ pv_all, int64_t nstreams, int64_t bins, double alpha,
-		    unsigned long long *__restrict__ tally)
+		    unsigned long long *__restrict__ tally, const unsigned long long *__restrict__ limit)
 {
 	const int64_t idx = (int64_t) blockIdx.x * 256 + threadIdx.x;
 	if (idx >= nstreams * P.npv)
 		return;
+	if (limit != nullptr && (unsigned long long) (idx / P.npv) >= *limit)
+		return;					/* "-F a" batch: the text ended before this stream was complete */
 	const int q = (int) (idx % P.npv);
 	const double p_value = pv_all[idx];
 	if (p_value == NONP)
@@ -480,10 +482,11 @@ assess_finish_kernel(DevParams P, int64_t bins, double alpha, double level, doub
 	out[q] = m;
 }
 
-cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally)
+cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally,
+				const unsigned long long *d_limit)
 {
 	const int64_t total = L.nstreams * P.npv;
-	assess_tally_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, L.stream>>>(P, L.d_pv, L.nstreams, bins, alpha, d_tally);
+	assess_tally_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, L.stream>>>(P, L.d_pv, L.nstreams, bins, alpha, d_tally, d_limit);
 	return cudaGetLastError();
 }
 

@@ -272,45 +272,81 @@ read_streams(struct sts_state *s, uint8_t *dst, long streams)
 
 /*
  * invokeTestSuite(): replaces the pthread pool of handleFileBasedBitStreams/testBits.  Seek rule of
- * the reference (utilities.c:1526): job `jobnum` starts at byte jobnum * n * iterations / 8.
+ * the reference (utilities.c:1511, :1526): job `jobnum` starts at byte jobnum * n * iterations / 8 of a raw
+ * file, at character jobnum * n * iterations of an ASCII file; standard input ("-") is never seeked (:1500).
  * Pipelined two deep: while the GPU tests batch k, the host reads and submits batch k+1 from the other
  * pinned buffer, then runs the record keeping of batch k.
+ *
+ * ASCII files go to the GPU as text (stsgpu_submit_ascii): iteration k is the first n digits at or after
+ * character base_seek + k n, the reference's per-iteration fseek (utilities.c:1682-1683).  ASCII on standard
+ * input cannot seek, there the digits are consumed in sequence and packed here (read_streams), as the
+ * reference does for stdin.
  */
 void
 sts_invokeTestSuite(struct sts_state *s)
 {
-	const long nb = s->tp.n / 8;
+	const long n = s->tp.n;
+	const long nb = n / 8;
 	const long B = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
-	s->streamFile = fopen(s->randomDataPath, "rb");
+	const bool from_stdin = (strcmp(s->randomDataPath, "-") == 0);
+	const bool gpu_ascii = (s->dataFormat == STS_FORMAT_ASCII_01) && !from_stdin;
+	s->streamFile = from_stdin ? stdin : fopen(s->randomDataPath, "rb");
 	if (s->streamFile == NULL)
 		sts_err(210, __func__, "cannot open data file %s: %s", s->randomDataPath, strerror(errno));
-	if (s->jobnum > 0) {
-		const long per_stream = (s->dataFormat == STS_FORMAT_RAW_BINARY) ? nb : s->tp.n;
-		if (fseek(s->streamFile, s->jobnum * per_stream * s->tp.numOfBitStreams, SEEK_SET) != 0)
-			sts_err(211, __func__, "cannot seek to job %ld", s->jobnum);
+	long base_seek = 0, file_size = 0;
+	if (!from_stdin) {
+		const long per_stream = (s->dataFormat == STS_FORMAT_RAW_BINARY) ? nb : n;
+		base_seek = s->jobnum * per_stream * s->tp.numOfBitStreams;
+		if (fseek(s->streamFile, 0, SEEK_END) != 0 || (file_size = ftell(s->streamFile)) < 0 ||
+		    fseek(s->streamFile, base_seek, SEEK_SET) != 0)
+			sts_err(211, __func__, "cannot seek to job %ld in %s", s->jobnum, s->randomDataPath);
 	}
+	const size_t buf_bytes = gpu_ascii ? (size_t) (B + 1) * (size_t) n : (size_t) B * (size_t) nb;
 	uint8_t *buf[2];
 	for (int i = 0; i < 2; i++) {
-		buf[i] = stsgpu_host_alloc((size_t) B * (size_t) nb);
+		buf[i] = stsgpu_host_alloc(buf_bytes);
 		if (buf[i] == NULL)
-			sts_err(212, __func__, "cannot allocate pinned read buffer of %ld bytes", B * nb);
+			sts_err(212, __func__, "cannot allocate pinned read buffer of %zu bytes", buf_bytes);
 	}
 	struct sts_thread_state ts = { 0, s, 0, NULL };
 	const long total = s->tp.numOfBitStreams;
 	long submitted = 0, done = 0;
 	int w = 0, eof = 0;
+	long waited = 0;				/* batches completed: batch k was read into buf[k & 1] */
+	long batch_want[2] = { 0, 0 };
+	bool window_at_eof[2] = { false, false };	/* ASCII: did the text window of the batch in buf[i] end at EOF? */
+	bool short_seen = false;
 	for (;;) {
 		/* keep two batches in flight: the read and the upload of one overlap the kernels of the other */
 		while (stsgpu_pending(s->engine) < 2 && !eof && submitted < total) {
 			const long want = (total - submitted) < B ? (total - submitted) : B;
-			const long have = read_streams(s, buf[w & 1], want);
-			if (have < want)
-				eof = 1;
-			if (have <= 0)
-				break;
-			int rc = stsgpu_submit(s->engine, buf[w & 1], have, submitted);
+			long have = want;
+			int rc;
+			if (gpu_ascii) {
+				const long off = base_seek + submitted * n;
+				long len = (want + 1) * n;
+				if (off >= file_size) {
+					fprintf(stderr, "Warning: insufficient data in %s, %ld bits were read\n", s->randomDataPath, 0L);
+					eof = 1;
+					break;
+				}
+				window_at_eof[w & 1] = (off + len >= file_size);
+				if (off + len > file_size)
+					len = file_size - off;
+				if (fseek(s->streamFile, off, SEEK_SET) != 0 || (long) fread(buf[w & 1], 1, (size_t) len, s->streamFile) != len)
+					sts_err(213, __func__, "cannot read %ld characters at offset %ld of %s", len, off, s->randomDataPath);
+				rc = stsgpu_submit_ascii(s->engine, (const char *) buf[w & 1], len, want, submitted);
+			} else {
+				have = read_streams(s, buf[w & 1], want);
+				if (have < want)
+					eof = 1;
+				if (have <= 0)
+					break;
+				rc = stsgpu_submit(s->engine, buf[w & 1], have, submitted);
+			}
 			if (rc != STSGPU_OK)
 				sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+			batch_want[w & 1] = have;
 			submitted += have;
 			w++;
 		}
@@ -321,6 +357,24 @@ sts_invokeTestSuite(struct sts_state *s)
 			sts_err(216, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
 		int64_t bn, bf;
 		stsgpu_results(s->engine, &bn, &bf, &s->batch_pvals, NULL, NULL);
+		if (gpu_ascii) {
+			const int slot = (int) (waited & 1);
+			int64_t complete, bad;
+			stsgpu_ascii_status(s->engine, &complete, &bad);
+			if (bad >= 0 && !short_seen)
+				sts_err(214, __func__, "found a character different than 1 or 0 in the sequence: %c (offset %ld)",
+					buf[slot][bad], (long) (base_seek + bf * n + bad));
+			if (complete < batch_want[slot] && !short_seen) {
+				short_seen = true;
+				if (!window_at_eof[slot])
+					sts_err(217, __func__, "more than %ld white-space characters inside one batch of %s", n,
+						s->randomDataPath);
+				fprintf(stderr, "Warning: insufficient data in %s: iteration %ld is incomplete\n", s->randomDataPath,
+					(long) (bf + complete));
+				eof = 1;		/* every later iteration starts further into the text and is incomplete too */
+			}
+		}
+		waited++;
 		s->batch_first = (long) bf;
 		s->batch_count = (long) bn;
 		for (long k = 0; k < (long) bn; k++) {		/* iteration order: reproducible .pvalues */
@@ -334,7 +388,8 @@ sts_invokeTestSuite(struct sts_state *s)
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
 	for (int i = 0; i < 2; i++)
 		stsgpu_host_free(buf[i]);
-	fclose(s->streamFile);
+	if (!from_stdin)
+		fclose(s->streamFile);
 	s->streamFile = NULL;
 }
 

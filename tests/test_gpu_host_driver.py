@@ -134,3 +134,38 @@ def test_short_file_is_fatal(tmp_path):
     open(p, "wb").write(b"\x00" * 1000)
     r = subprocess.run([STSB200, "-i", "1", "-w", str(tmp_path / "s"), p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 213                   # utilities.c:1789-1791: a short raw read is fatal
+
+
+def test_ascii_file_with_line_breaks_matches_reference(tmp_path, oracle):
+    """-F a through the GPU packer: in a file with line breaks the reference's per-iteration seek makes consecutive
+    streams overlap; stsb200 must produce the reference's p-values, not those of a sequential reader.  Also -j 1."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    bits = np.unpackbits(oracle.lcg_bytes(0, 7))
+    txt = "\n".join("".join("01"[b] for b in bits[i:i + 80]) for i in range(0, bits.size, 80)) + "\n"
+    ap = str(tmp_path / "ascii.txt")
+    open(ap, "w").write(txt)
+    for job in ("0", "1"):
+        wg, wr = str(tmp_path / ("g" + job)), str(tmp_path / ("r" + job))
+        run([STSB200, "-m", "i", "-i", "3", "-j", job, "-B", "2", "-F", "a", "-w", wg, ap])
+        run([REF, "-v", "0", "-m", "i", "-T", "1", "-i", "3", "-j", job, "-F", "a", "-w", wr, ap])
+        name = "sts.000%s.3.1048576.pvalues" % job
+        a, b = read_pvalues(os.path.join(wg, name)), read_pvalues(os.path.join(wr, name))
+        assert sorted(a) == sorted(b) == list(range(1, 16))
+        for t in range(1, 16):
+            assert a[t].shape == b[t].shape
+            assert rel_err(a[t], b[t]).max() <= 1e-9, "test %d" % t
+
+
+def test_stdin_input(lcg8, tmp_path):
+    """datafile "-": standard input is read in sequence, never seeked (utilities.c:1500-1502)"""
+    w = str(tmp_path / "stdin")
+    with open(lcg8, "rb") as f:
+        r = subprocess.run([STSB200, "-m", "i", "-i", "2", "-t", "1,2,4", "-F", "r", "-w", w, "-"], stdin=f,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout[-2000:]
+    pv = read_pvalues(os.path.join(w, "sts.0000.2.1048576.pvalues"))
+    g = load_golden("lcg_default_8")
+    for t in (1, 2, 4):
+        ref = g["pv_%d" % t][:2]
+        assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9

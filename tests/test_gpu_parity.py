@@ -339,3 +339,80 @@ def test_small_streams_against_oracle(sts, oracle, n):
         assert eng.layout.enabled_mask == oracle.layout(oracle.make_params(test_mask=mask, **prm)).enabled_mask
         pv, st, w = eng.run(raw, streams)
         compare_with_oracle(sts, oracle, eng, mask, prm, raw, streams, pv, st, w)
+
+
+def ascii_text(bits, line):
+    """'0'/'1' characters with a line break after every `line` digits (none if line == 0)"""
+    ch = (bits + ord("0")).astype(np.uint8)
+    if not line:
+        return ch
+    rows = -(-ch.size // line)
+    pad = np.full(rows * line, ord(" "), dtype=np.uint8)
+    pad[:ch.size] = ch
+    out = np.concatenate([pad.reshape(rows, line), np.full((rows, 1), ord("\n"), dtype=np.uint8)], axis=1).reshape(-1)
+    return out
+
+
+def seek_rule_streams(text, n, streams):
+    """parseBitsASCIIInput (utilities.c:1682-1697): iteration k = the first n digits at or after character k n"""
+    out = np.zeros((streams, n // 8), dtype=np.uint8)
+    complete = 0
+    for k in range(streams):
+        w = text[k * n:]
+        d = w[(w == ord("0")) | (w == ord("1"))][:n] - ord("0")
+        if d.size < n:
+            break
+        out[k] = np.packbits(d)
+        complete += 1
+    return out, complete
+
+
+@pytest.mark.parametrize("line", [0, 64, 61, 1])
+def test_ascii_input_is_packed_like_the_reference_reads_it(sts, oracle, line):
+    """-F a on the device (stsgpu_submit_ascii): packed rows bit-exact against the reference's seek rule, records equal
+    to the raw path on those rows; line breaks every 64 / 61 / 1 digits, or none"""
+    n, streams = 1 << 16, 5
+    mask = (1 << 1) | (1 << 3) | (1 << 4) | (1 << 12) | (1 << 13) | (1 << 14)
+    bits = np.unpackbits(oracle.lcg_bytes(0, 1))[:n * (streams + 1) + 999]
+    text = ascii_text(bits, line)[:(streams + 1) * n]
+    want, complete = seek_rule_streams(text, n, streams)
+    assert complete == streams
+    eng = sts.Engine(max_streams=streams, n=n, test_mask=mask)
+    eng.submit_ascii(text, streams, 0)
+    eng.wait()
+    assert eng.ascii_status() == (streams, -1)
+    pv_a, st_a, _ = eng.results()
+    got = eng.download_input(streams).reshape(streams, n // 8)
+    assert (got == want).all(), "packed rows differ from the reference's reading of the text"
+    eng.submit(want.reshape(-1), streams, 0)
+    eng.wait()
+    pv_r, st_r, _ = eng.results()
+    assert (st_a == st_r).all() and (pv_a == pv_r).all()
+    if line == 0:                               # without white space the streams are the file's bits in sequence
+        assert (want.reshape(-1) == np.packbits(bits[:n * streams])).all()
+    eng.close()
+
+
+def test_ascii_input_short_text_and_bad_characters(sts, oracle):
+    n, streams = 1 << 16, 4
+    bits = np.unpackbits(oracle.lcg_bytes(0, 1))[:n * 3 + 100]
+    text = ascii_text(bits, 64)
+    _, complete = seek_rule_streams(text, n, streams)
+    assert 0 < complete < streams
+    eng = sts.Engine(max_streams=streams, n=n, test_mask=1 << 1)
+    eng.submit_ascii(text, streams, 0)
+    eng.wait()
+    assert eng.ascii_status() == (complete, -1)
+    assert eng.results()[0].shape[0] == complete          # only the complete leading streams are reported
+    bad = text.copy()
+    bad[70000] = ord("x")
+    bad[100] = ord("2")                          # the reference would store a 2 in epsilon; here it is an error
+    eng.submit_ascii(bad, 1, 0)
+    eng.wait()
+    assert eng.ascii_status() == (1, 100)
+    late = text.copy()
+    late[n + n // 64 + 5] = ord("x")             # after stream 0's last digit: the reference never scans it
+    eng.submit_ascii(late, 1, 0)
+    eng.wait()
+    assert eng.ascii_status() == (1, -1)
+    eng.close()
