@@ -271,6 +271,13 @@ typedef struct stsgpu_metric {
 /* start (or restart) tallying: uniformity_bins = tp.uniformity_bins (sqrt(iterations), or 10 with -O),
  * alpha = tp.alpha (0.01), uniformity_level = tp.uniformity_level (0.0001); needs an idle engine */
 int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t uniformity_bins, double alpha, double uniformity_level);
+/*
+ * Assess-only mode (-m a, read_from_p_val_file utilities.c:2051-2165): add `count` p-values of test `test` read from a
+ * .pvalues file (host memory, file order = iteration-major) to the tallies; `first_index` is the position of pvals[0]
+ * in that test's p-value sequence, so a file of any size can be streamed through a small buffer in pieces.
+ * Value i lands in column pv_off[test] + (first_index + i) mod pv_cnt[test].  Synchronous.
+ */
+int stsgpu_assess_add(stsgpu_ctx *ctx, int test, const double *pvals, int64_t count, int64_t first_index);
 /* sum the tallies of all ranks of the communicator into every rank (NCCL all-reduce); no-op for one rank */
 int stsgpu_assess_reduce(stsgpu_ctx *ctx);
 /*

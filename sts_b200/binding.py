@@ -22,7 +22,7 @@ EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_g
            "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
-           "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
+           "stsgpu_assess_add", "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
            "stsgpu_kernel_count", "stsgpu_kernel_info", "stsgpu_last_batch_ms", "stsgpu_launch_count",
            "stsgpu_debug_pattern_histogram", "stsgpu_strerror", "stsgpu_last_error", "stsgpu_abi_version"]
 
@@ -100,6 +100,7 @@ def load_library():
     lib.stsgpu_gather_pvals.argtypes = [vp, i32, C.POINTER(vp)]
     lib.stsgpu_comm_barrier.argtypes = [vp]
     lib.stsgpu_assess_begin.argtypes = [vp, i64, C.c_double, C.c_double]
+    lib.stsgpu_assess_add.argtypes = [vp, i32, vp, i64, i64]
     lib.stsgpu_assess_reduce.argtypes = [vp]
     lib.stsgpu_assess_finish.argtypes = [vp, C.POINTER(Metric), vp]
     lib.stsgpu_set_profiling.argtypes = [vp, i32]
@@ -283,6 +284,11 @@ class Engine:
     def assess_begin(self, bins, alpha=0.01, uniformity_level=0.0001):
         self._assess_bins = bins
         self._ck(self.lib.stsgpu_assess_begin(self.h, bins, alpha, uniformity_level), "assess_begin")
+
+    def assess_add(self, test, pvals, first_index=0):
+        """p-values of one test in .pvalues order (iteration-major) into the tallies"""
+        v = np.ascontiguousarray(pvals, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.stsgpu_assess_add(self.h, test, v.ctypes.data, v.size, first_index), "assess_add")
 
     def assess_reduce(self):
         self._ck(self.lib.stsgpu_assess_reduce(self.h), "assess_reduce")

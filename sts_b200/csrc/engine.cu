@@ -553,6 +553,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 	}
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
 	cudaFree(ctx->d_tally);
+	cudaFree(ctx->d_assess_stage);
 	for (int i = 0; i < 12; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
 	delete ctx;
@@ -922,6 +923,40 @@ extern "C" int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t bins, double alpha, 
 	ctx->assess_alpha = alpha;
 	ctx->assess_level = level;
 	ctx->assessing = true;
+	return STSGPU_OK;
+}
+
+#define ASSESS_STAGE_VALUES ((int64_t) 1 << 22)		/* 32 MiB of p-values per copy */
+
+extern "C" int stsgpu_assess_add(stsgpu_ctx *ctx, int test, const double *pvals, int64_t count, int64_t first_index)
+{
+	if (ctx == NULL || pvals == NULL || count < 0 || first_index < 0 || test < 1 || test > 15)
+		return STSGPU_E_INVAL;
+	if (!ctx->assessing || ctx->submit_seq != ctx->wait_seq) {
+		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_assess_add needs stsgpu_assess_begin and an idle engine");
+		return STSGPU_E_STATE;
+	}
+	if (!((ctx->lay.enabled_mask >> test) & 1u)) {
+		snprintf(ctx->err, sizeof(ctx->err), "test %d is not enabled in this engine", test);
+		return STSGPU_E_RANGE;
+	}
+	if (cudaSetDevice(ctx->device) != cudaSuccess)
+		return STSGPU_E_CUDA;
+	if (ctx->d_assess_stage == nullptr)
+		CK(cudaMalloc((void **) &ctx->d_assess_stage, (size_t) ASSESS_STAGE_VALUES * sizeof(double)));
+	for (int64_t done = 0; done < count;) {
+		const int64_t c = (count - done < ASSESS_STAGE_VALUES) ? count - done : ASSESS_STAGE_VALUES;
+		CK(cudaMemcpyAsync(ctx->d_assess_stage, pvals + done, (size_t) c * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
+		cudaError_t e = launch_assess_add(ctx->P, ctx->lay.pv_off[test], ctx->lay.pv_cnt[test], ctx->d_assess_stage, c, first_index + done, ctx->assess_bins,
+						  ctx->assess_alpha, ctx->d_tally, ctx->s_main);
+		if (e != cudaSuccess) {
+			set_err(ctx, "assess add", e);
+			return STSGPU_E_CUDA;
+		}
+		CK(cudaStreamSynchronize(ctx->s_main));		/* `pvals` may be pageable and is reused by the caller */
+		ctx->launches += 1;
+		done += c;
+	}
 	return STSGPU_OK;
 }
 

@@ -78,6 +78,7 @@ struct stsgpu_ctx {
 	int64_t assess_bins = 0;
 	double assess_alpha = 0.01, assess_level = 0.0001;
 	unsigned long long *d_tally = nullptr;
+	double *d_assess_stage = nullptr;	/* stsgpu_assess_add: staging for p-values read from files */
 
 	bool profiling = false;
 	int64_t launches = 0;
@@ -98,6 +99,8 @@ cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCt
 cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally,
 				const unsigned long long *d_limit);
+cudaError_t launch_assess_add(const DevParams &P, int pv_off, int pv_cnt, const double *d_vals, int64_t count, int64_t first_index,
+			      int64_t bins, double alpha, unsigned long long *d_tally, cudaStream_t stream);
 cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha, double level, double lgam, const unsigned long long *d_tally,
 				 stsgpu_metric *d_out, cudaStream_t stream);
 cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);

@@ -408,17 +408,10 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
  * Assessment tallies (include/stsgpu.h, stsgpu_assess_*): frequency.c:828-894, one thread per
  * (stream, p-value column) of the batch; per column [sampleCount, toolow, freq[bins]].
  */
-__global__ void __launch_bounds__(256)
-assess_tally_kernel(DevParams P, const double *__restrict__ pv_all, int64_t nstreams, int64_t bins, double alpha,
-		    unsigned long long *__restrict__ tally, const unsigned long long *__restrict__ limit)
+/* one p-value of column q into the tallies (the loop body of frequency.c:828-894) */
+__device__ __forceinline__ void tally_one(const DevParams &P, int q, double p_value, int64_t bins, double alpha,
+					  unsigned long long *__restrict__ tally)
 {
-	const int64_t idx = (int64_t) blockIdx.x * 256 + threadIdx.x;
-	if (idx >= nstreams * P.npv)
-		return;
-	if (limit != nullptr && (unsigned long long) (idx / P.npv) >= *limit)
-		return;					/* "-F a" batch: the text ended before this stream was complete */
-	const int q = (int) (idx % P.npv);
-	const double p_value = pv_all[idx];
 	if (p_value == NONP)
 		return;					/* the test was not possible for this iteration */
 	const int e12 = P.pv_off[STSGPU_TEST_RND_EXCURSION], e13 = P.pv_off[STSGPU_TEST_RND_EXCURSION_VAR];
@@ -438,6 +431,31 @@ assess_tally_kernel(DevParams P, const double *__restrict__ pv_all, int64_t nstr
 	else
 		b = 0;
 	atomicAdd(&t[2 + b], 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+assess_tally_kernel(DevParams P, const double *__restrict__ pv_all, int64_t nstreams, int64_t bins, double alpha,
+		    unsigned long long *__restrict__ tally, const unsigned long long *__restrict__ limit)
+{
+	const int64_t idx = (int64_t) blockIdx.x * 256 + threadIdx.x;
+	if (idx >= nstreams * P.npv)
+		return;
+	if (limit != nullptr && (unsigned long long) (idx / P.npv) >= *limit)
+		return;					/* "-F a" batch: the text ended before this stream was complete */
+	tally_one(P, (int) (idx % P.npv), pv_all[idx], bins, alpha, tally);
+}
+
+/* p-values of ONE test in .pvalues order (iteration-major, utilities.c:1967-2024): value i of the test's sequence
+ * belongs to column pv_off[test] + i mod pv_cnt[test] */
+__global__ void __launch_bounds__(256)
+assess_add_kernel(DevParams P, int pv_off, int pv_cnt, const double *__restrict__ vals, int64_t count, int64_t first_index, int64_t bins,
+		  double alpha, unsigned long long *__restrict__ tally)
+{
+	const int64_t i = (int64_t) blockIdx.x * 256 + threadIdx.x;
+	if (i >= count)
+		return;
+	const int q = pv_off + (int) ((first_index + i) % pv_cnt);
+	tally_one(P, q, vals[i], bins, alpha, tally);
 }
 
 /* frequency.c:631-700 and :739-757, one thread per column */
@@ -487,6 +505,14 @@ cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t 
 {
 	const int64_t total = L.nstreams * P.npv;
 	assess_tally_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, L.stream>>>(P, L.d_pv, L.nstreams, bins, alpha, d_tally, d_limit);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_assess_add(const DevParams &P, int pv_off, int pv_cnt, const double *d_vals, int64_t count, int64_t first_index,
+			      int64_t bins, double alpha, unsigned long long *d_tally, cudaStream_t stream)
+{
+	assess_add_kernel<<<(unsigned) ((count + 255) / 256), 256, 0, stream>>>(P, pv_off, pv_cnt, d_vals, count, first_index, bins, alpha,
+										 d_tally);
 	return cudaGetLastError();
 }
 

@@ -5,6 +5,8 @@
  * serial.c:229-249) without changing any p_val content.
  */
 #define _GNU_SOURCE
+#define _DEFAULT_SOURCE
+#include <dirent.h>
 #include <errno.h>
 #include <math.h>
 #include <stdarg.h>
@@ -100,7 +102,7 @@ sts_init(struct sts_state *s)
 	p.device = s->device;
 	p.n = s->tp.n;
 	p.max_streams = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
-	if (p.max_streams < 1)
+	if (p.max_streams < 1 || s->runMode == STS_MODE_ASSESS_ONLY)
 		p.max_streams = 1;
 	p.test_mask = 0;
 	for (int t = 1; t <= STS_NUMOFTESTS; t++)
@@ -119,10 +121,11 @@ sts_init(struct sts_state *s)
 	if (rc != STSGPU_OK)		/* no CPU fallback: fatal, like every error in the reference */
 		sts_err(50, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(NULL));
 	stsgpu_get_layout(s->engine, &s->layout);
-	if (s->runMode == STS_MODE_ITERATE_AND_ASSESS) {
-		/* parse_args.c:791-803: bins = sqrt(iterations) unless -P 8 was given; -O forces 10 */
+	if (s->runMode != STS_MODE_ITERATE_ONLY) {
+		/* parse_args.c:791-803: bins = sqrt(iterations) unless -P 8 was given; -O forces 10.  With -m a the
+		 * iterations are those of -i (default 1), not the count found in the file names (parse_args.c:848) */
 		if (!s->uniformityBinsFlag)
-			s->tp.uniformityBins = (long) sqrt((double) s->tp.numOfBitStreams);
+			s->tp.uniformityBins = (long) sqrt((double) (s->binsIterations > 0 ? s->binsIterations : s->tp.numOfBitStreams));
 		if (s->legacy_output)
 			s->tp.uniformityBins = 10;
 		if (s->tp.uniformityBins < 1)
@@ -416,16 +419,205 @@ sts_write_p_val_to_file(struct sts_state *s)
 		sts_err(232, __func__, "error in renaming %s to %s", work, fin);
 }
 
+/* does `name` look like sts.<job>.<iterations>.<n>.pvalues (parse_args.c:866-898)?  returns the iterations or -1 */
+static long
+p_val_file_iterations(const char *name, long n)
+{
+	char *copy = strdup(name), *rest = copy, *tok[5];
+	int k = 0;
+	while (k < 5 && (tok[k] = strsep(&rest, ".")) != NULL)
+		k++;
+	long it = -1;
+	if (k == 5 && strcmp(tok[0], "sts") == 0 && strcmp(tok[4], "pvalues") == 0 && atoi(tok[3]) == n)
+		it = atoi(tok[2]);
+	free(copy);
+	return it;
+}
+
+/* parse_args.c:837-921: the iterations of an assess-only run are the sum of those in the matching file names */
+void
+sts_find_p_val_files(struct sts_state *s)
+{
+	DIR *dir = opendir(s->pvalues_dir);
+	if (dir == NULL)
+		sts_err(1, __func__, "Could not open the directory: %s", s->pvalues_dir);
+	struct dirent *e;
+	s->tp.numOfBitStreams = 0;
+	while ((e = readdir(dir)) != NULL) {
+		const long it = p_val_file_iterations(e->d_name, s->tp.n);
+		if (it > 0)
+			s->tp.numOfBitStreams += it;
+	}
+	closedir(dir);
+}
+
 /*
- * metrics() (driver.c:475): the table every X_metrics prints in legacy format (e.g. frequency.c:700-735):
+ * read_from_p_val_file (utilities.c:2051-2165): records of {int64 test, int64 count, count doubles}.  The
+ * reference appends every value to state->p_val (64 bytes per template p-value); here each file is streamed
+ * through one 8 MiB buffer into the tallies on the GPU, so memory does not grow with the run.
+ */
+void
+sts_read_from_p_val_file(struct sts_state *s)
+{
+	enum { CHUNK = 1 << 20 };
+	double *buf = malloc(CHUNK * sizeof(double));
+	if (buf == NULL)
+		sts_err(232, __func__, "cannot allocate the p-value read buffer");
+	long seen[STS_NUMOFTESTS + 1] = { 0 };
+	DIR *dir = opendir(s->pvalues_dir);
+	if (dir == NULL)
+		sts_err(1, __func__, "Could not open the directory: %s", s->pvalues_dir);
+	struct dirent *e;
+	while ((e = readdir(dir)) != NULL) {
+		if (p_val_file_iterations(e->d_name, s->tp.n) <= 0)
+			continue;
+		char path[4096];
+		snprintf(path, sizeof(path), "%s/%s", s->pvalues_dir, e->d_name);
+		FILE *f = fopen(path, "rb");
+		if (f == NULL) {
+			fprintf(stderr, "Warning: skipping p-value file due to error in opening p-value file: %s\n", e->d_name);
+			continue;
+		}
+		long test_num = 0, count;
+		do {
+			if (fread(&test_num, sizeof(test_num), 1, f) != 1 || fread(&count, sizeof(count), 1, f) != 1)
+				break;
+			if (test_num < 1 || test_num > STS_NUMOFTESTS || count < 0) {
+				fprintf(stderr, "Warning: skipping p-value file, bad record header in %s\n", e->d_name);
+				break;
+			}
+			const bool on = s->testVector[test_num];
+			for (long done = 0; done < count;) {
+				const long c = (count - done) < CHUNK ? (count - done) : CHUNK;
+				if ((long) fread(buf, sizeof(double), (size_t) c, f) != c) {
+					fprintf(stderr, "Warning: EOF while reading pvalue[%ld] from file: %s\n", done, e->d_name);
+					count = done;
+					test_num = STS_NUMOFTESTS;
+					break;
+				}
+				if (on) {
+					int rc = stsgpu_assess_add(s->engine, (int) test_num, buf, c, seen[test_num] + done);
+					if (rc != STSGPU_OK)
+						sts_err(53, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+				}
+				done += c;
+			}
+			seen[test_num] += count;
+		} while (test_num < STS_NUMOFTESTS);		/* utilities.c:2153: the record of test 15 ends a file */
+		fclose(f);
+	}
+	closedir(dir);
+	free(buf);
+	for (int t = 1; t <= STS_NUMOFTESTS; t++)
+		if (s->testVector[t] && seen[t] != s->tp.numOfBitStreams * s->partitionCount[t])
+			fprintf(stderr, "Warning: %s[%d]: %ld p-values found != bit streams: %ld\n", sts_testNames[t], t, seen[t],
+				s->tp.numOfBitStreams * s->partitionCount[t]);
+}
+
+/* finishMetricTestsSentence, driver.c:1112-1146 */
+enum { PASSED_BOTH = 0, FAILED_UNIFORMITY = 1, FAILED_PROPORTION = 2, FAILED_BOTH = 3 };
+static const char *const verdict_sentence[4] = {
+	"passed both the analyses.\n", "FAILED the uniformity analysis.\n", "FAILED the proportion analysis.\n",
+	"FAILED both the analyses.\n"
+};
+
+static int
+verdict_of(const stsgpu_metric *m)		/* e.g. frequency.c:757-766 */
+{
+	if (!m->proportion_passed && !m->uniformity_passed)
+		return FAILED_BOTH;
+	if (!m->proportion_passed)
+		return FAILED_PROPORTION;
+	if (!m->uniformity_passed)
+		return FAILED_UNIFORMITY;
+	return PASSED_BOTH;
+}
+
+/* result.txt, the non-legacy report of driver.c:676-1100, from the verdicts of the GPU tallies */
+static void
+write_result_txt(struct sts_state *s, const stsgpu_metric *m)
+{
+	static const char *const single[STS_NUMOFTESTS + 1] = {
+		NULL, "Frequency", "Block Frequency", NULL, "Runs", "Longest Run of Ones", "Binary Matrix Rank",
+		"Discrete Fourier Transform", NULL, "Overlapping Template Matching", "Maurer's Universal Statistical",
+		"Approximate Entropy", NULL, NULL, NULL, "Linear Complexity"
+	};
+	static const char *const multi[STS_NUMOFTESTS + 1] = {
+		NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, "Non-overlapping Template Matching", NULL, NULL, NULL,
+		"Random Excursions", "Random Excursions Variant", NULL, NULL
+	};
+	static const char *const sep = "- - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - "
+				       "- - - - - - - - - - - - - - -\n";
+	char path[4096];
+	snprintf(path, sizeof(path), "%s/result.txt", s->workDir);
+	FILE *f = fopen(path, "w");
+	if (f == NULL)
+		sts_err(54, __func__, "cannot open %s: %s", path, strerror(errno));
+	long total = 0;
+	for (int t = 1; t <= STS_NUMOFTESTS; t++)
+		if (s->testVector[t])
+			total += s->partitionCount[t];
+	const char *source = "--SOME_FILE--";
+	if (s->randomDataPath != NULL)
+		source = strcmp(s->randomDataPath, "-") == 0 ? "((standard input))" :
+			 (strcmp(s->randomDataPath, "/dev/null") != 0 ? s->randomDataPath : "--UNKNOWN--");
+	fprintf(f, "A total of %ld tests (some of the %d tests actually consist of multiple sub-tests)\n"
+		   "were conducted to evaluate the randomness of %ld bitstreams of %ld bits from:\n\n\t%s\n\n",
+		total, STS_NUMOFTESTS, s->tp.numOfBitStreams, s->tp.n, source);
+	if (s->runMode == STS_MODE_ASSESS_ONLY)
+		fprintf(f, "using the p-values from the following files:\n\n\t%s/sts.*.*.%ld.pvalues\n\n", s->pvalues_dir, s->tp.n);
+	fprintf(f, "%s\n"
+		   "The numerous empirical results of these tests were then interpreted with\nan "
+		   "examination of the proportion of sequences that pass a statistical test\n"
+		   "(proportion analysis) and the distribution of p-values to check for uniformity\n"
+		   "(uniformity analysis). The results were the following:\n\n"
+		   "\t%ld/%ld tests passed successfully both the analyses.\n"
+		   "\t%ld/%ld tests did not pass successfully both the analyses.\n\n"
+		   "%s\nHere are the results of the single tests:\n",
+		sep, s->successful_tests, total, total - s->successful_tests, total, sep);
+	for (int t = 1; t <= STS_NUMOFTESTS; t++) {
+		if (!s->testVector[t])
+			continue;
+		const stsgpu_metric *mt = m + s->layout.pv_off[t];
+		if (single[t] != NULL) {
+			fprintf(f, "\n - The \"%s\" test %s", single[t], verdict_sentence[verdict_of(mt)]);
+		} else if (multi[t] != NULL) {
+			long by[4] = { 0, 0, 0, 0 };
+			for (int j = 0; j < s->partitionCount[t]; j++)
+				by[verdict_of(mt + j)]++;
+			static const int order[4] = { PASSED_BOTH, FAILED_PROPORTION, FAILED_UNIFORMITY, FAILED_BOTH };
+			bool first = true;
+			for (int k = 0; k < 4; k++) {
+				if (by[order[k]] <= 0)
+					continue;
+				fprintf(f, first ? "\n - " : "   ");
+				first = false;
+				fprintf(f, "%ld/%d of the \"%s\" tests %s", by[order[k]], s->partitionCount[t], multi[t],
+					verdict_sentence[order[k]]);
+			}
+		} else {			/* CumulativeSums and Serial: two named sub-tests */
+			const char *name = (t == 3) ? "Cumulative Sums" : "Serial";
+			const char *a = (t == 3) ? "forward" : "first", *b = (t == 3) ? "backward" : "second";
+			fprintf(f, "\n - The \"%s\" (%s) test %s", name, a, verdict_sentence[verdict_of(mt)]);
+			fprintf(f, "   The \"%s\" (%s) test %s", name, b, verdict_sentence[verdict_of(mt + 1)]);
+		}
+	}
+	fprintf(f, "\n%s\nThe missing tests (if any) were whether disabled manually by the user or disabled\n"
+		   "at run time due to input size requirements not satisfied by this run.\n\n", sep);
+	fclose(f);
+}
+
+/*
+ * metrics() (driver.c:475): with -O the table every X_metrics prints in legacy format (e.g. frequency.c:700-735):
  * bin counts, uniformity p-value, passCount/sampleCount, test name, one line per p-value column in test
- * order, written to workDir/finalAnalysisReport.txt under the reference's header.  The tallies come from
- * the GPU (stsgpu_assess_*), so no p-value has to be kept for this.
+ * order, written to workDir/finalAnalysisReport.txt under the reference's header; without -O the summary of
+ * workDir/result.txt (driver.c:676-1100).  The tallies come from the GPU (stsgpu_assess_*), so no p-value has
+ * to be kept for this.
  */
 void
 sts_metrics(struct sts_state *s)
 {
-	if (s->runMode != STS_MODE_ITERATE_AND_ASSESS)
+	if (s->runMode == STS_MODE_ITERATE_ONLY)
 		return;
 	const int npv = s->layout.npv;
 	const long bins = s->tp.uniformityBins;
@@ -436,6 +628,16 @@ sts_metrics(struct sts_state *s)
 	int rc = stsgpu_assess_finish(s->engine, m, freq);
 	if (rc != STSGPU_OK)
 		sts_err(53, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+	s->successful_tests = 0;
+	for (int q = 0; q < npv; q++)
+		if (verdict_of(m + q) == PASSED_BOTH)
+			s->successful_tests++;
+	if (!s->legacy_output) {
+		write_result_txt(s, m);
+		free(m);
+		free(freq);
+		return;
+	}
 	char path[4096];
 	snprintf(path, sizeof(path), "%s/finalAnalysisReport.txt", s->workDir);
 	FILE *f = fopen(path, "w");
@@ -444,7 +646,7 @@ sts_metrics(struct sts_state *s)
 	fprintf(f, "------------------------------------------------------------------------------\n");
 	fprintf(f, "RESULTS FOR THE UNIFORMITY OF P-VALUES AND THE PROPORTION OF PASSING SEQUENCES\n");
 	fprintf(f, "------------------------------------------------------------------------------\n");
-	fprintf(f, "   generator is <%s>\n", s->randomDataPath);
+	fprintf(f, "   generator is <%s>\n", s->randomDataPath ? s->randomDataPath : "--SOME_FILE--");
 	fprintf(f, "------------------------------------------------------------------------------\n");
 	for (long i = 0; i < bins; i++) {
 		char name[32];
@@ -491,5 +693,6 @@ sts_destroy(struct sts_state *s)
 	}
 	free(s->workDir);
 	free(s->randomDataPath);
-	s->workDir = s->randomDataPath = NULL;
+	free(s->pvalues_dir);
+	s->workDir = s->randomDataPath = s->pvalues_dir = NULL;
 }

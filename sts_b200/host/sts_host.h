@@ -66,6 +66,9 @@ struct sts_state {
 	bool uniformityBinsFlag;		/* -P 8 given (parse_args.c:993) */
 	char *workDir;				/* -w */
 	char *randomDataPath;			/* data file */
+	char *pvalues_dir;			/* -d: directory of sts.*.*.<n>.pvalues files (-m a) */
+	long binsIterations;			/* the -i value sqrt(iterations) bins are derived from (parse_args.c:791-793) */
+	long successful_tests;			/* p-value columns that passed both analyses (e.g. frequency.c:765) */
 	FILE *streamFile;
 	/* counters of defs.h:437-441 */
 	long count[STS_NUMOFTESTS + 1], valid[STS_NUMOFTESTS + 1], success[STS_NUMOFTESTS + 1],
@@ -104,6 +107,8 @@ void sts_init(struct sts_state *state);					/* driver.c:205 */
 void sts_invokeTestSuite(struct sts_state *state);			/* utilities.c:1433 */
 void sts_iterate(struct sts_thread_state *thread_state);		/* driver.c:395 */
 void sts_write_p_val_to_file(struct sts_state *state);			/* utilities.c:1938 */
+void sts_find_p_val_files(struct sts_state *state);			/* parse_args.c:837-921: count the iterations of -d dir */
+void sts_read_from_p_val_file(struct sts_state *state);			/* utilities.c:2051: here streamed into the GPU tallies */
 void sts_destroy(struct sts_state *state);				/* driver.c:1153 */
 
 /* fatal error in the reference's style: message + exit(code) (debug.c:267) */

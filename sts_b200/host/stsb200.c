@@ -1,9 +1,11 @@
 /*
  * stsb200.c - the reference's main() sequence (src/sts.c:317-399) for the hot path:
- *     parse_args -> init -> invokeTestSuite -> write_p_val_to_file -> destroy
+ *     parse_args -> init -> invokeTestSuite -> write_p_val_to_file -> metrics -> destroy      (-m b, -m i)
+ *     parse_args -> init -> read_from_p_val_file -> metrics -> destroy                         (-m a -d dir)
  * with the reference's flag letters and meanings for everything the path needs
- * (-i -S -P -T -j -m -F -t -w -v -I; parse_args.c:426-957).  Assessment (result.txt) is not rebuilt:
- * run the reference itself on the .pvalues this program writes:  sts -m a -d <workDir> ...
+ * (-i -S -P -T -j -m -d -F -t -w -v -I -O; parse_args.c:426-957).  The assessment (result.txt, or the table of
+ * finalAnalysisReport.txt with -O) comes from tallies kept on the GPU; the .pvalues files stay compatible with the
+ * reference's own sts -m a -d <workDir>.
  */
 #define _GNU_SOURCE
 #include <getopt.h>
@@ -13,11 +15,12 @@
 
 static const char *usage =
 	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
-	"               [-I reportCycle] [-O] [-w workDir] [-F r|a] [-j jobnum] [-m b|i] [-T threads] [-B batch] [-D device] datafile\n"
+	"               [-I reportCycle] [-O] [-w workDir] [-F r|a] [-j jobnum] [-m b|i|a] [-d pvaluesdir] [-T threads]\n"
+	"               [-B batch] [-D device] [datafile | -]\n"
 	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
 	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b also writes the\n"
-	"  uniformity / proportion table of the reference's legacy report (finalAnalysisReport.txt), tallied on the GPU;\n"
-	"  assess with the reference: sts -m a -d workDir -i <total iterations> ...\n";
+	"  reference's result.txt (with -O the table of its legacy finalAnalysisReport.txt), tallied on the GPU;\n"
+	"  -m a -d dir assesses the .pvalues files of earlier -m i runs, streamed through the GPU tallies in bounded memory.\n";
 
 int
 main(int argc, char **argv)
@@ -26,7 +29,7 @@ main(int argc, char **argv)
 	sts_defaultstate(&st);
 	int opt;
 	char *brkt, *phrase;
-	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:Oh")) != -1) {
+	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:d:Oh")) != -1) {
 		switch (opt) {
 		case 'v': st.debuglevel = atoi(optarg); break;
 		case 't':
@@ -71,8 +74,10 @@ main(int argc, char **argv)
 		case 'm':
 			if (optarg[0] == 'b') st.runMode = STS_MODE_ITERATE_AND_ASSESS;
 			else if (optarg[0] == 'i') st.runMode = STS_MODE_ITERATE_ONLY;
-			else sts_err(1, __func__, "-m %s: only b and i run on the GPU; use the reference's sts -m a to assess", optarg);
+			else if (optarg[0] == 'a') st.runMode = STS_MODE_ASSESS_ONLY;
+			else sts_err(1, __func__, "-m mode: %s must be b, i or a", optarg);
 			break;
+		case 'd': free(st.pvalues_dir); st.pvalues_dir = strdup(optarg); break;
 		case 'T': st.numberOfThreads = atol(optarg); break;
 		case 'B': st.batchStreams = atol(optarg); break;
 		case 'D': st.device = atoi(optarg); break;
@@ -83,20 +88,34 @@ main(int argc, char **argv)
 			return opt == 'h' ? 0 : 1;
 		}
 	}
-	if (optind != argc - 1) {
+	if (optind == argc - 1)
+		st.randomDataPath = strdup(argv[optind]);
+	else if (optind != argc || st.runMode != STS_MODE_ASSESS_ONLY) {	/* parse_args.c:706-732: -m a needs no data file */
 		fputs(usage, stderr);
 		return 1;
 	}
-	st.randomDataPath = strdup(argv[optind]);
 	if (!st.testVectorFlag)				/* parse_args.c: no -t means all tests */
 		for (int i = 1; i <= STS_NUMOFTESTS; i++) st.testVector[i] = true;
 	if (st.tp.numOfBitStreams < 1)
 		sts_err(1, __func__, "-i iterations: %ld must be > 0", st.tp.numOfBitStreams);
+	st.binsIterations = st.tp.numOfBitStreams;
 
+	if (st.runMode == STS_MODE_ASSESS_ONLY) {	/* sts.c:352-383: init, read the p-value files, metrics */
+		if (st.pvalues_dir == NULL)
+			sts_err(1, __func__, "-m a requires -d pvaluesdir");
+		sts_find_p_val_files(&st);
+		sts_init(&st);
+		sts_read_from_p_val_file(&st);
+		sts_metrics(&st);
+		if (st.debuglevel > 0)
+			printf("assessed %ld iterations from %s/sts.*.*.%ld.pvalues\n", st.tp.numOfBitStreams, st.pvalues_dir, st.tp.n);
+		sts_destroy(&st);
+		return 0;
+	}
 	sts_init(&st);
 	sts_invokeTestSuite(&st);
 	sts_write_p_val_to_file(&st);
-	sts_metrics(&st);			/* -m b: the uniformity / proportion table, tallied on the GPU */
+	sts_metrics(&st);			/* -m b: result.txt (or, with -O, the legacy table), tallied on the GPU */
 	if (st.debuglevel > 0) {
 		for (int t = 1; t <= STS_NUMOFTESTS; t++)
 			if (st.testVector[t])

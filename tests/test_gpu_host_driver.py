@@ -169,3 +169,38 @@ def test_stdin_input(lcg8, tmp_path):
     for t in (1, 2, 4):
         ref = g["pv_%d" % t][:2]
         assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9
+
+
+def test_result_txt_of_mode_b_identical_to_reference(tmp_path, oracle):
+    """stsb200 -m b writes result.txt itself (verdicts from the GPU tallies): same body as the reference's"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    p = str(tmp_path / "lcg32.bin")
+    oracle.lcg_bytes(0, 32).tofile(p)
+    run([STSB200, "-m", "b", "-i", "32", "-F", "r", "-B", "20", "-w", str(tmp_path / "gpu"), p])
+    run([REF, "-v", "0", "-i", "32", "-F", "r", "-w", str(tmp_path / "ref"), p])
+    a, b = result_body(str(tmp_path / "gpu" / "result.txt")), result_body(str(tmp_path / "ref" / "result.txt"))
+    assert "tests passed successfully both the analyses" in a
+    assert a == b
+    head = open(str(tmp_path / "gpu" / "result.txt")).read().split("- - - -")[0]
+    assert "A total of 188 tests" in head and "32 bitstreams of 1048576 bits" in head and p in head
+
+
+def test_assess_only_mode_streams_pvalues_files(lcg8, tmp_path):
+    """stsb200 -m a -d DIR: the .pvalues files of two -m i jobs, streamed through the GPU tallies, give the
+    result.txt of the reference's own sts -m a on the same directory (with and without -i: the bins quirk)"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    d = str(tmp_path / "pv")
+    os.makedirs(d)
+    for k in range(2):
+        run([STSB200, "-m", "i", "-j", str(k), "-i", "4", "-F", "r", "-w", d, lcg8])
+    open(os.path.join(d, "sts.0000.4.4096.pvalues"), "wb").write(b"")        # other n: must be ignored
+    for extra in (["-i", "8"], []):
+        tag = "i" if extra else "noi"
+        run([STSB200, "-m", "a", "-d", d, "-w", str(tmp_path / ("gpu_" + tag))] + extra)
+        run([REF, "-v", "0", "-m", "a", "-d", d, "-w", str(tmp_path / ("ref_" + tag))] + extra)
+        a = open(str(tmp_path / ("gpu_" + tag) / "result.txt")).read()
+        b = open(str(tmp_path / ("ref_" + tag) / "result.txt")).read()
+        assert "8 bitstreams of 1048576 bits" in a
+        assert a == b                                # whole file: same source line (--SOME_FILE--) and directory
