@@ -229,6 +229,11 @@ int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_t nstreams)
 int stsgpu_download_input(stsgpu_ctx *ctx, uint8_t *raw, int64_t nstreams);
 
 /* ---- pinned host memory for the caller's read buffers -------------------------------------- */
+/*
+ * Page-locked memory for `raw` / `text` buffers, placed on the NUMA node of the calling thread's current CUDA
+ * device (the device of the context created last) so that uploads do not cross sockets; STSGPU_NUMA=0 in the
+ * environment leaves placement to the OS.
+ */
 void *stsgpu_host_alloc(size_t bytes);
 void stsgpu_host_free(void *p);
 
