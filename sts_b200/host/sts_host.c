@@ -202,24 +202,108 @@ DEF_ITERATE(RandomExcursionsVariant, 13) DEF_ITERATE(Serial, 14) DEF_ITERATE(Lin
 
 static void noop_state(struct sts_state *s) { (void) s; }
 
+/* data_filename_format, utilities.c:479-538: "data.txt" unless the partition count exceeds a
+ * power of ten: the digits are the largest d with 10^d < partitionCount (0 -> data.txt, else data%0<d>d.txt), so 2 and
+ * 8 partitions all write data.txt, 18 write data1 .. data18 and 148 write data01 .. data148 */
+static void
+data_filename(char *out, size_t len, int partitionCount, int j)
+{
+	int digits = 0;
+	if (partitionCount >= 2)
+		for (digits = 9; digits > 0; --digits)			/* MAX_DATA_DIGITS */
+			if (pow(10.0, digits) < (double) partitionCount)
+				break;
+	if (digits < 1)
+		snprintf(out, len, "data.txt");
+	else
+		snprintf(out, len, "data%0*d.txt", digits, j);
+}
+
+static void
+print_p_value(FILE *f, double p_value)			/* e.g. Frequency_print_p_value, frequency.c:378-408 */
+{
+	if (p_value == STS_NON_P_VALUE)
+		fprintf(f, "__INVALID__\n");
+	else
+		fprintf(f, "%f\n", p_value);
+}
+
+/*
+ * The -s files every X_print writes that come from p-values alone (e.g. frequency.c:424-618):
+ * <workDir>/<TestName>/results.txt with every p-value in order, and, for tests with several p-values per
+ * iteration, data*.txt with the values of one partition each.  stats.txt (the per-iteration intermediate values
+ * of each test's private struct) is not produced.
+ */
+static void
+print_test(struct sts_state *s, int t)
+{
+	if (!s->testVector[t] || !s->resultstxtFlag)
+		return;
+	const long count = s->p_val[t].count;
+	const int parts = s->partitionCount[t];
+	if (count != s->tp.numOfBitStreams * parts)
+		sts_err(74, __func__, "print driver interface for %s[%d] called with p_val count: %ld != %ld*%d",
+			sts_testNames[t], t, count, s->tp.numOfBitStreams, parts);
+	char dir[4096], path[4400], name[64];
+	snprintf(dir, sizeof(dir), "%s/%s", s->workDir, sts_testNames[t]);
+	struct stat sb;
+	if (stat(dir, &sb) != 0 && mkdir(dir, 0777) != 0)
+		sts_err(74, __func__, "cannot create %s: %s", dir, strerror(errno));
+	snprintf(path, sizeof(path), "%s/results.txt", dir);
+	FILE *f = fopen(path, "w");
+	if (f == NULL)
+		sts_err(74, __func__, "cannot open %s: %s", path, strerror(errno));
+	for (long i = 0; i < count; i++)
+		print_p_value(f, s->p_val[t].v[i]);
+	fclose(f);
+	if (parts > 1) {
+		for (int j = 0; j < parts; j++) {
+			data_filename(name, sizeof(name), parts, j + 1);
+			snprintf(path, sizeof(path), "%s/%s", dir, name);
+			f = fopen(path, "w");		/* openTruncate: with data.txt the last partition wins, as in the reference */
+			if (f == NULL)
+				sts_err(74, __func__, "cannot open %s: %s", path, strerror(errno));
+			for (long i = j; i < count; i += parts)
+				print_p_value(f, s->p_val[t].v[i]);
+			fclose(f);
+		}
+	}
+}
+
+#define DEF_PRINT(NAME, T) static void NAME##_print(struct sts_state *s) { print_test(s, T); }
+DEF_PRINT(Frequency, 1) DEF_PRINT(BlockFrequency, 2) DEF_PRINT(CumulativeSums, 3) DEF_PRINT(Runs, 4)
+DEF_PRINT(LongestRunOfOnes, 5) DEF_PRINT(Rank, 6) DEF_PRINT(DiscreteFourierTransform, 7)
+DEF_PRINT(NonOverlappingTemplateMatchings, 8) DEF_PRINT(OverlappingTemplateMatchings, 9)
+DEF_PRINT(Universal, 10) DEF_PRINT(ApproximateEntropy, 11) DEF_PRINT(RandomExcursions, 12)
+DEF_PRINT(RandomExcursionsVariant, 13) DEF_PRINT(Serial, 14) DEF_PRINT(LinearComplexity, 15)
+
+/* driver.c:434-470 */
+void
+sts_print(struct sts_state *s)
+{
+	for (int i = 1; i <= STS_NUMOFTESTS; i++)
+		if (s->testVector[i] == true && sts_testDriver[i].print != NULL)
+			sts_testDriver[i].print(s);
+}
+
 /* the plugin table, driver.c:63-192: same order, same five phases */
 const struct sts_driver sts_testDriver[STS_NUMOFTESTS + 1] = {
 	{ NULL, NULL, NULL, NULL, NULL },
-	{ noop_state, Frequency_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, BlockFrequency_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, CumulativeSums_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, Runs_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, LongestRunOfOnes_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, Rank_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, DiscreteFourierTransform_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, NonOverlappingTemplateMatchings_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, OverlappingTemplateMatchings_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, Universal_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, ApproximateEntropy_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, RandomExcursions_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, RandomExcursionsVariant_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, Serial_iterate, noop_state, noop_state, noop_state },
-	{ noop_state, LinearComplexity_iterate, noop_state, noop_state, noop_state },
+	{ noop_state, Frequency_iterate, Frequency_print, noop_state, noop_state },
+	{ noop_state, BlockFrequency_iterate, BlockFrequency_print, noop_state, noop_state },
+	{ noop_state, CumulativeSums_iterate, CumulativeSums_print, noop_state, noop_state },
+	{ noop_state, Runs_iterate, Runs_print, noop_state, noop_state },
+	{ noop_state, LongestRunOfOnes_iterate, LongestRunOfOnes_print, noop_state, noop_state },
+	{ noop_state, Rank_iterate, Rank_print, noop_state, noop_state },
+	{ noop_state, DiscreteFourierTransform_iterate, DiscreteFourierTransform_print, noop_state, noop_state },
+	{ noop_state, NonOverlappingTemplateMatchings_iterate, NonOverlappingTemplateMatchings_print, noop_state, noop_state },
+	{ noop_state, OverlappingTemplateMatchings_iterate, OverlappingTemplateMatchings_print, noop_state, noop_state },
+	{ noop_state, Universal_iterate, Universal_print, noop_state, noop_state },
+	{ noop_state, ApproximateEntropy_iterate, ApproximateEntropy_print, noop_state, noop_state },
+	{ noop_state, RandomExcursions_iterate, RandomExcursions_print, noop_state, noop_state },
+	{ noop_state, RandomExcursionsVariant_iterate, RandomExcursionsVariant_print, noop_state, noop_state },
+	{ noop_state, Serial_iterate, Serial_print, noop_state, noop_state },
+	{ noop_state, LinearComplexity_iterate, LinearComplexity_print, noop_state, noop_state },
 };
 
 /* driver.c:395-425 */

@@ -63,6 +63,7 @@ struct sts_state {
 	long reportCycle;			/* -I */
 	int debuglevel;				/* -v */
 	bool legacy_output;			/* -O: 10 uniformity bins, finalAnalysisReport.txt (parse_args.c:585, :792-803) */
+	bool resultstxtFlag;			/* -s: results.txt and data*.txt per test (parse_args.c:606) */
 	bool uniformityBinsFlag;		/* -P 8 given (parse_args.c:993) */
 	char *workDir;				/* -w */
 	char *randomDataPath;			/* data file */
@@ -106,6 +107,7 @@ void sts_change_params(struct sts_state *state, long num, long value, double d_v
 void sts_init(struct sts_state *state);					/* driver.c:205 */
 void sts_invokeTestSuite(struct sts_state *state);			/* utilities.c:1433 */
 void sts_iterate(struct sts_thread_state *thread_state);		/* driver.c:395 */
+void sts_print(struct sts_state *state);				/* driver.c:434 */
 void sts_write_p_val_to_file(struct sts_state *state);			/* utilities.c:1938 */
 void sts_find_p_val_files(struct sts_state *state);			/* parse_args.c:837-921: count the iterations of -d dir */
 void sts_read_from_p_val_file(struct sts_state *state);			/* utilities.c:2051: here streamed into the GPU tallies */

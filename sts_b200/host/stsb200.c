@@ -3,7 +3,7 @@
  *     parse_args -> init -> invokeTestSuite -> write_p_val_to_file -> metrics -> destroy      (-m b, -m i)
  *     parse_args -> init -> read_from_p_val_file -> metrics -> destroy                         (-m a -d dir)
  * with the reference's flag letters and meanings for everything the path needs
- * (-i -S -P -T -j -m -d -F -t -w -v -I -O; parse_args.c:426-957).  The assessment (result.txt, or the table of
+ * (-i -S -P -T -j -m -d -F -t -w -v -I -O -s; parse_args.c:426-957).  The assessment (result.txt, or the table of
  * finalAnalysisReport.txt with -O) comes from tallies kept on the GPU; the .pvalues files stay compatible with the
  * reference's own sts -m a -d <workDir>.
  */
@@ -15,7 +15,7 @@
 
 static const char *usage =
 	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
-	"               [-I reportCycle] [-O] [-w workDir] [-F r|a] [-j jobnum] [-m b|i|a] [-d pvaluesdir] [-T threads]\n"
+	"               [-I reportCycle] [-O] [-s] [-w workDir] [-F r|a] [-j jobnum] [-m b|i|a] [-d pvaluesdir] [-T threads]\n"
 	"               [-B batch] [-D device] [datafile | -]\n"
 	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
 	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b also writes the\n"
@@ -29,7 +29,7 @@ main(int argc, char **argv)
 	sts_defaultstate(&st);
 	int opt;
 	char *brkt, *phrase;
-	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:d:Oh")) != -1) {
+	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:d:Osh")) != -1) {
 		switch (opt) {
 		case 'v': st.debuglevel = atoi(optarg); break;
 		case 't':
@@ -82,6 +82,7 @@ main(int argc, char **argv)
 		case 'B': st.batchStreams = atol(optarg); break;
 		case 'D': st.device = atoi(optarg); break;
 		case 'O': st.legacy_output = true; break;
+		case 's': st.resultstxtFlag = true; break;
 		case 'h':
 		default:
 			fputs(usage, stderr);
@@ -114,6 +115,7 @@ main(int argc, char **argv)
 	}
 	sts_init(&st);
 	sts_invokeTestSuite(&st);
+	sts_print(&st);				/* -s */
 	sts_write_p_val_to_file(&st);
 	sts_metrics(&st);			/* -m b: result.txt (or, with -O, the legacy table), tallied on the GPU */
 	if (st.debuglevel > 0) {

@@ -204,3 +204,23 @@ def test_assess_only_mode_streams_pvalues_files(lcg8, tmp_path):
         b = open(str(tmp_path / ("ref_" + tag) / "result.txt")).read()
         assert "8 bitstreams of 1048576 bits" in a
         assert a == b                                # whole file: same source line (--SOME_FILE--) and directory
+
+
+def test_dash_s_results_and_data_files_identical_to_reference(lcg8, tmp_path):
+    """-s: <TestName>/results.txt and data*.txt (the p-value files of every X_print, including the reference's file
+    naming: data.txt for 2 and 8 partitions, data1..18, data01..148) byte for byte; stats.txt is not produced"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/sts not shipped")
+    wg, wr = str(tmp_path / "g"), str(tmp_path / "r")
+    run([STSB200, "-s", "-m", "b", "-i", "3", "-F", "r", "-w", wg, lcg8])
+    run([REF, "-v", "0", "-s", "-T", "1", "-i", "3", "-F", "r", "-w", wr, lcg8])
+    seen = 0
+    for root, _, files in os.walk(wr):
+        for f in files:
+            if f == "results.txt" or f.startswith("data"):
+                rel = os.path.relpath(os.path.join(root, f), wr)
+                mine = os.path.join(wg, rel)
+                assert os.path.exists(mine), rel
+                assert open(mine).read() == open(os.path.join(root, f)).read(), rel
+                seen += 1
+    assert seen == 15 + 1 + 148 + 1 + 18 + 1       # results.txt x 15, cusum, templates, excursions, variant, serial
