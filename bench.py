@@ -215,7 +215,7 @@ def main():
 
     B = args.streams
     K, W = args.steps, max(args.warmup, 3)
-    DEPTH = 2							# batches in flight (stsgpu_params.pipeline_depth)
+    DEPTH = int(os.environ.get("STS_BENCH_DEPTH", "3"))		# batches in flight (stsgpu_params.pipeline_depth)
     eng = sts_b200.Engine(device=local, max_streams=B, pipeline_depth=DEPTH)	# raises if libstsgpu.so or the GPU is missing
     lay = eng.layout
     if world > 1:
@@ -354,7 +354,7 @@ def main():
                 "in_region_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes_region.items()},
                 "note": "kernel_ms / all_kernel_groups_ms: CUDA events around each kernel group with the groups "
                         "serialised (3 steps right after the timed region, same inputs); in_region_ms: the same "
-                        "events inside the timed region, where two batches and two streams per batch overlap; "
+                        "events inside the timed region, where several batches and five streams per batch overlap; "
                         "see profiles/ for ncu"}
 
     cpu = None
@@ -374,7 +374,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu_per_step": B, "bits_per_stream": N_BITS,
                        "l2": "input per step (128 MiB) exceeds L2; the FFT intermediate (8 GiB per step) flushes it",
-                       "pipeline": "%d batches in flight per GPU (copies of one overlap kernels of the other)" % DEPTH,
+                       "pipeline": "%d batches in flight per GPU (the upload of one overlaps the kernels of the others)" % DEPTH,
                        "sharding": "rank r tests streams [r*B,(r+1)*B), p-values gathered to rank 0 over NCCL"},
             "device_ms_per_step": dev_step_ms,
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -114,7 +114,7 @@ sts_init(struct sts_state *s)
 	p.apen_m = (int32_t) s->tp.approximateEntropyBlockLength;
 	p.serial_m = (int32_t) s->tp.serialBlockLength;
 	p.linear_complexity_M = s->tp.linearComplexitySequenceLength;
-	p.pipeline_depth = 2;					/* sts_invokeTestSuite keeps two batches in flight */
+	p.pipeline_depth = STS_PIPELINE_DEPTH;			/* sts_invokeTestSuite keeps this many batches in flight */
 	if ((s->tp.n % 8) != 0)					/* parse_args.c:939 */
 		sts_err(1, __func__, "bitcount(n): %ld must be a multiple of 8", s->tp.n);
 	int rc = stsgpu_create(&p, &s->engine);
@@ -361,8 +361,10 @@ read_streams(struct sts_state *s, uint8_t *dst, long streams)
  * invokeTestSuite(): replaces the pthread pool of handleFileBasedBitStreams/testBits.  Seek rule of
  * the reference (utilities.c:1511, :1526): job `jobnum` starts at byte jobnum * n * iterations / 8 of a raw
  * file, at character jobnum * n * iterations of an ASCII file; standard input ("-") is never seeked (:1500).
- * Pipelined two deep: while the GPU tests batch k, the host reads and submits batch k+1 from the other
- * pinned buffer, then runs the record keeping of batch k.
+ * Pipelined STS_PIPELINE_DEPTH (3) deep: while the GPU tests batch k, batch k+1 is already uploaded and the host
+ * reads and submits batch k+2 from the third pinned buffer, then runs the record keeping of batch k.  (With
+ * two in flight the upload of the newest batch - 2.4 ms of the 9.7 ms a batch takes - leaves the GPU with
+ * the kernels of a single batch: measured 103.5 against 108.9 Gbit/s end to end.)
  *
  * ASCII files go to the GPU as text (stsgpu_submit_ascii): iteration k is the first n digits at or after
  * character base_seek + k n, the reference's per-iteration fseek (utilities.c:1682-1683).  ASCII on standard
@@ -389,8 +391,9 @@ sts_invokeTestSuite(struct sts_state *s)
 			sts_err(211, __func__, "cannot seek to job %ld in %s", s->jobnum, s->randomDataPath);
 	}
 	const size_t buf_bytes = gpu_ascii ? (size_t) (B + 1) * (size_t) n : (size_t) B * (size_t) nb;
-	uint8_t *buf[2];
-	for (int i = 0; i < 2; i++) {
+	const int depth = gpu_ascii ? 2 : STS_PIPELINE_DEPTH;	/* text is 8 bytes per tested byte: PCIe bound at any depth */
+	uint8_t *buf[STS_PIPELINE_DEPTH];
+	for (int i = 0; i < depth; i++) {
 		buf[i] = stsgpu_host_alloc(buf_bytes);
 		if (buf[i] == NULL)
 			sts_err(212, __func__, "cannot allocate pinned read buffer of %zu bytes", buf_bytes);
@@ -399,13 +402,13 @@ sts_invokeTestSuite(struct sts_state *s)
 	const long total = s->tp.numOfBitStreams;
 	long submitted = 0, done = 0;
 	int w = 0, eof = 0;
-	long waited = 0;				/* batches completed: batch k was read into buf[k & 1] */
-	long batch_want[2] = { 0, 0 };
-	bool window_at_eof[2] = { false, false };	/* ASCII: did the text window of the batch in buf[i] end at EOF? */
+	long waited = 0;				/* batches completed: batch k was read into buf[k % depth] */
+	long batch_want[STS_PIPELINE_DEPTH] = { 0 };
+	bool window_at_eof[STS_PIPELINE_DEPTH] = { false };	/* ASCII: did the text window of the batch in buf[i] end at EOF? */
 	bool short_seen = false;
 	for (;;) {
-		/* keep two batches in flight: the read and the upload of one overlap the kernels of the other */
-		while (stsgpu_pending(s->engine) < 2 && !eof && submitted < total) {
+		/* keep `depth` batches in flight: the read and the upload of one overlap the kernels of the others */
+		while (stsgpu_pending(s->engine) < depth && !eof && submitted < total) {
 			const long want = (total - submitted) < B ? (total - submitted) : B;
 			long have = want;
 			int rc;
@@ -417,23 +420,23 @@ sts_invokeTestSuite(struct sts_state *s)
 					eof = 1;
 					break;
 				}
-				window_at_eof[w & 1] = (off + len >= file_size);
+				window_at_eof[w % depth] = (off + len >= file_size);
 				if (off + len > file_size)
 					len = file_size - off;
-				if (fseek(s->streamFile, off, SEEK_SET) != 0 || (long) fread(buf[w & 1], 1, (size_t) len, s->streamFile) != len)
+				if (fseek(s->streamFile, off, SEEK_SET) != 0 || (long) fread(buf[w % depth], 1, (size_t) len, s->streamFile) != len)
 					sts_err(213, __func__, "cannot read %ld characters at offset %ld of %s", len, off, s->randomDataPath);
-				rc = stsgpu_submit_ascii(s->engine, (const char *) buf[w & 1], len, want, submitted);
+				rc = stsgpu_submit_ascii(s->engine, (const char *) buf[w % depth], len, want, submitted);
 			} else {
-				have = read_streams(s, buf[w & 1], want);
+				have = read_streams(s, buf[w % depth], want);
 				if (have < want)
 					eof = 1;
 				if (have <= 0)
 					break;
-				rc = stsgpu_submit(s->engine, buf[w & 1], have, submitted);
+				rc = stsgpu_submit(s->engine, buf[w % depth], have, submitted);
 			}
 			if (rc != STSGPU_OK)
 				sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
-			batch_want[w & 1] = have;
+			batch_want[w % depth] = have;
 			submitted += have;
 			w++;
 		}
@@ -445,7 +448,7 @@ sts_invokeTestSuite(struct sts_state *s)
 		int64_t bn, bf;
 		stsgpu_results(s->engine, &bn, &bf, &s->batch_pvals, NULL, NULL);
 		if (gpu_ascii) {
-			const int slot = (int) (waited & 1);
+			const int slot = (int) (waited % depth);
 			int64_t complete, bad;
 			stsgpu_ascii_status(s->engine, &complete, &bad);
 			if (bad >= 0 && !short_seen)
@@ -473,7 +476,7 @@ sts_invokeTestSuite(struct sts_state *s)
 		done += (long) bn;
 	}
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < depth; i++)
 		stsgpu_host_free(buf[i]);
 	if (!from_stdin)
 		fclose(s->streamFile);

@@ -26,6 +26,7 @@
 #include "../../include/stsgpu.h"
 
 #define STS_NUMOFTESTS 15
+#define STS_PIPELINE_DEPTH 3		/* batches in flight in sts_invokeTestSuite (stsgpu_params.pipeline_depth) */
 #define STS_NON_P_VALUE (-99999999.0)
 
 enum sts_run_mode { STS_MODE_ITERATE_AND_ASSESS = 0, STS_MODE_ITERATE_ONLY = 1, STS_MODE_ASSESS_ONLY = 2 };	/* -m b/i/a */
