@@ -198,12 +198,67 @@ lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__res
 }
 
 /*
- * Long blocks (M > 1022, up to the reference's limit of 5000): one block per WARP, lane l holding words
- * [l WPL, (l + 1) WPL) of the three arrays in registers.  With one block per warp the discrepancy and the
- * length test are warp-uniform, so the updates are real (uniform) branches instead of masks: a step is
- * WPL AND-XORs, one redux.sync, WPL funnel shifts and one shuffle for the bit that crosses lanes.
+ * Long blocks (M > 1022, up to the reference's limit of 5000): one block per WARP.  Word i of the three arrays
+ * lives in lane i mod 32, register slot i / 32 (cyclic), so that the window of live words - the same bound as in
+ * the per-thread kernel: indices [min(N0 - L + 1, L), N + 2] - covers whole slots: for random input about
+ * N / 2048 .. N / 1024, i.e. 1-3 of the 5 slots of M = 5000 instead of all of them.  With one block per warp the
+ * discrepancy and the length test are warp-uniform, so the updates are real (uniform) branches instead of
+ * masks: a step is one AND-XOR, one rotate-shuffle and one funnel shift per live slot plus one redux.sync.
+ * The slot range is re-derived every 256 steps and selects one of WPL (WPL + 1) / 2 unrolled bodies.
  * (The per-thread local-memory kernel below took 83 % of a BASELINE config 4 batch.)
  */
+template <int WPL, int SLO, int SHI>
+__device__ __forceinline__ void lc_warp_steps(const uint32_t (&S)[WPL], uint32_t (&C)[WPL], uint32_t (&B)[WPL], int &L, int Na,
+					      int Nb, int lane)
+{
+	const int src = (lane + 31) & 31;
+	for (int N = Na; N < Nb; N++) {
+		uint32_t acc = 0;
+#pragma unroll
+		for (int j = SLO; j <= SHI; j++)
+			acc ^= C[j] & S[j];
+		const uint32_t d = (uint32_t) __popc(__reduce_xor_sync(0xffffffffu, acc)) & 1u;
+		if (d) {				/* linearComplexity.c:322-336 */
+			if (2 * L <= N) {
+#pragma unroll
+				for (int j = SLO; j <= SHI; j++) {
+					const uint32_t c_old = C[j];
+					C[j] = c_old ^ B[j];
+					B[j] = c_old;
+				}
+				L = N + 1 - L;
+			} else {
+#pragma unroll
+				for (int j = SLO; j <= SHI; j++)
+					C[j] ^= B[j];
+			}
+		}
+		/* advance to N + 1: word i takes the bit that leaves word i - 1 (lane - 1; for lane 0 lane 31 of the slot below) */
+		uint32_t below = 0;
+#pragma unroll
+		for (int j = SLO; j <= SHI; j++) {
+			const uint32_t c = C[j];
+			const uint32_t rot = __shfl_sync(0xffffffffu, c, src);
+			const uint32_t carry = (lane == 0) ? below : rot;
+			C[j] = (c >> 1) | (carry << 31);
+			below = rot;
+		}
+	}
+}
+
+template <int WPL, int SLO, int SHI>
+__device__ __forceinline__ void lc_warp_dispatch(int slo, int shi, const uint32_t (&S)[WPL], uint32_t (&C)[WPL], uint32_t (&B)[WPL],
+						 int &L, int Na, int Nb, int lane)
+{
+	if (slo == SLO && shi == SHI) {
+		lc_warp_steps<WPL, SLO, SHI>(S, C, B, L, Na, Nb, lane);
+	} else if constexpr (SLO < SHI) {
+		lc_warp_dispatch<WPL, SLO + 1, SHI>(slo, shi, S, C, B, L, Na, Nb, lane);
+	} else if constexpr (SHI + 1 < WPL) {
+		lc_warp_dispatch<WPL, 0, SHI + 1>(slo, shi, S, C, B, L, Na, Nb, lane);
+	}
+}
+
 template <int WPL>
 __global__ void __launch_bounds__(LC_THREADS)
 lc_kernel_warp(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__restrict__ class_lut,
@@ -223,7 +278,7 @@ lc_kernel_warp(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__re
 		uint32_t S[WPL], C[WPL], B[WPL];
 #pragma unroll
 		for (int j = 0; j < WPL; j++) {
-			const int i = lane * WPL + j;		/* word index; array index k <-> position k - 1 */
+			const int i = j * 32 + lane;		/* word index; array index k <-> position k - 1 */
 			uint32_t v = 0;
 			const int valid = M + 1 - 32 * i;	/* indices still inside the block */
 			if (valid > 0) {
@@ -240,37 +295,13 @@ lc_kernel_warp(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__re
 			B[0] = 0x80000000u;	/* b_0 at position -1 (index 0) */
 		}
 		int L = 0;
-		for (int N = 0; N < M; N++) {
-			uint32_t acc = 0;
-#pragma unroll
-			for (int j = 0; j < WPL; j++)
-				acc ^= C[j] & S[j];
-			const uint32_t d = (uint32_t) __popc(__reduce_xor_sync(0xffffffffu, acc)) & 1u;
-			if (d) {				/* linearComplexity.c:322-336 */
-				if (2 * L <= N) {
-#pragma unroll
-					for (int j = 0; j < WPL; j++) {
-						const uint32_t c_old = C[j];
-						C[j] = c_old ^ B[j];
-						B[j] = c_old;
-					}
-					L = N + 1 - L;
-				} else {
-#pragma unroll
-					for (int j = 0; j < WPL; j++)
-						C[j] ^= B[j];
-				}
-			}
-			/* advance to N + 1: shift the whole array by one position */
-			uint32_t carry = __shfl_up_sync(0xffffffffu, C[WPL - 1], 1);
-			if (lane == 0)
-				carry = 0;
-#pragma unroll
-			for (int j = 0; j < WPL; j++) {
-				const uint32_t c = C[j];
-				C[j] = (c >> 1) | (carry << 31);
-				carry = c;
-			}
+		/* phases end where the top index N + 2 of the advanced array reaches a multiple of 256 */
+		for (int Na = 0; Na < M;) {
+			const int Nb = min(M, ((Na + 2) / 256 + 1) * 256 - 2);
+			const int slo = min(Na - L + 1, L) >> 10;	/* lowest live index, as in lc_phases */
+			const int shi = min((Nb + 1) >> 10, WPL - 1);
+			lc_warp_dispatch<WPL, 0, 0>(slo, shi, S, C, B, L, Na, Nb, lane);
+			Na = Nb;
 		}
 		if (lane == 0)
 			atomicAdd(&cls[class_lut[L]], 1u);
