@@ -5,7 +5,7 @@
  * sequential double-precision sum of 128000 terms at L = 7 whose rounding depends on the order.
  * To reproduce the reference's value bit for bit the kernel
  *   - finds every distance i - T[.] exactly (integers): a warp takes 32 consecutive L-bit blocks
- *     (one "row"), L ballots resolve repeats inside the row and a shared-memory table T[2^L]
+ *     (one "row"), `match.any` resolves repeats inside the row and a shared-memory table T[2^L]
  *     carries the last occurrence across rows (table starts at 0 like the reference's memset,
  *     universal.c:327);
  *   - looks the term up in a table of log(d) / log(2.0) computed ON THE HOST with the reference's
@@ -95,12 +95,11 @@ universal_kernel(DevParams P, const uint32_t *__restrict__ in, const unsigned lo
 				const int off = ((rg + r4) * 32 + lane) * L;	/* bit offset inside the super row */
 				const uint32_t hi = bswap32(buf[off >> 5]), lo = bswap32(buf[(off >> 5) + 1]);
 				v[r4] = __funnelshift_l(lo, hi, off & 31) >> (32 - L);
-#ifdef UNI_MATCH_ANY
+#ifndef UNI_BALLOT
 				const uint32_t same = __match_any_sync(0xffffffffu, v[r4]);
 #else
-				/* lanes holding the same L-bit pattern: one ballot per pattern bit.  Alone this is slower than MATCH.ANY
-				 * (kernel 1.07 -> 1.25 ms) but the pipelined batch, where the warp shares its SM with the FFT and
-				 * LinearComplexity CTAs, measured 1 % faster (9.68 against 9.82 ms); -DUNI_MATCH_ANY selects the other */
+				/* one ballot per pattern bit instead of MATCH.ANY: measured 1.27 against 1.07 ms for the kernel alone
+				 * (twice the issue slots) and no difference beyond noise for the pipelined batch */
 				uint32_t same = 0xffffffffu;
 				for (int b = 0; b < L; b++) {
 					const uint32_t bal = __ballot_sync(0xffffffffu, (v[r4] >> b) & 1u);
