@@ -34,13 +34,20 @@ cudaError_t launch_dft_1e6(const DevParams &P, const LaunchCtx &L, const DftPlan
 
 
 /*
- * A Stockham pass of radix R with the butterflies held in registers: a thread owns up to GDFT_MAXB
- * butterflies of the pass (work items tid, tid + T, ...), reads their inputs, applies the pass's
+ * A Stockham pass of radix R with the butterflies held in registers: a thread owns up to GDFT_PTS / R
+ * butterflies of the pass (16 / R for the power-of-two radices; work items tid, tid + T, ...), reads their inputs, applies the pass's
  * twiddles W_(Ns R)^(k r) (table entry (r - 1) Ns + k, k = b mod Ns) and the butterfly, and after a
  * barrier writes the outputs at ((b - k) R + k + r Ns) of the SAME buffer.  The first pass reads from
  * global memory (packed bits / the intermediate Y), the last pass of the columns writes Y.
  */
-#define GDFT_MAXB 2
+#define GDFT_PTS 20			/* points a thread holds across the barrier of a pass */
+/* butterflies per thread: two in the kernels for power-of-two lengths (WIDE = false), GDFT_PTS / R (16 / R for the
+ * power-of-two radices) in the kernels for mixed lengths.  Measured alternatives for the mixed kernels (ms per 1024
+ * streams at n = 10^7 / 400000 / 983040): this rule 188 / 5.9 / 17.3; 2 of radix 10 / 8 and 4 of the others
+ * 189 / 7.4 / 21.2; at most 10 points 208 / 7.4 / 18.7; the previous two-butterfly rule 298 / 8.8 / 17.6 */
+template <int R, bool WIDE> struct GdftMaxB {
+	static constexpr int value = !WIDE ? 2 : ((R == 8 || R == 4 || R == 2) ? 16 / R : GDFT_PTS / R);
+};
 
 template <int R> __device__ __forceinline__ void tw_bfly(double2 *v, const double2 *__restrict__ wtab, int Ns, int k)
 {
@@ -49,17 +56,21 @@ template <int R> __device__ __forceinline__ void tw_bfly(double2 *v, const doubl
 		for (int r = 1; r < R; r++)
 			v[r] = cmul(v[r], __ldg(wtab + (r - 1) * Ns + k));
 	}
-	bfly<R>(v);
+	if constexpr (R == 10)
+		bfly10(v);
+	else
+		bfly<R>(v);
 }
 
 /* ------------------------------------------------------------------------------------------ */
-template <int R>
+template <int R, bool WIDE>
 __device__ __forceinline__ void cols_pass(const DevParams &P, const DftPlan &D, const uint32_t *__restrict__ w, double2 *buf,
 					  double2 *__restrict__ Ys, int j20, int ps, int Ns)
 {
 	const int N1 = D.N1, N2 = D.N2, CW = D.cw, T = D.threads;
 	const int q = N1 / R, total = q * CW;
 	const bool first = (ps == 0), last = (ps == D.np1 - 1);
+	constexpr int GDFT_MAXB = GdftMaxB<R, WIDE>::value;
 	double2 v[GDFT_MAXB][R];
 	int kk[GDFT_MAXB];
 #pragma unroll
@@ -108,6 +119,7 @@ __device__ __forceinline__ void cols_pass(const DevParams &P, const DftPlan &D, 
 	__syncthreads();
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(512, 1)
 dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
@@ -120,24 +132,26 @@ dft_cols_kernel(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2
 	for (int ps = 0; ps < D.np1; ps++) {
 		const int R = D.rad1[ps];
 		switch (R) {
-		case 8: cols_pass<8>(P, D, w, buf, Ys, j20, ps, Ns); break;
-		case 5: cols_pass<5>(P, D, w, buf, Ys, j20, ps, Ns); break;
-		case 4: cols_pass<4>(P, D, w, buf, Ys, j20, ps, Ns); break;
-		case 3: cols_pass<3>(P, D, w, buf, Ys, j20, ps, Ns); break;
-		default: cols_pass<2>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 10: if constexpr (WIDE) cols_pass<10, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 8: cols_pass<8, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 5: cols_pass<5, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 4: cols_pass<4, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		case 3: cols_pass<3, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
+		default: cols_pass<2, WIDE>(P, D, w, buf, Ys, j20, ps, Ns); break;
 		}
 		Ns *= R;
 	}
 }
 
 /* ------------------------------------------------------------------------------------------ */
-template <int R>
+template <int R, bool WIDE>
 __device__ __forceinline__ void rows_pass(const DftPlan &D, const double2 *__restrict__ Ys, double2 *buf, int k1a, int k1b, int rows,
 					  int ps, int Ns)
 {
 	const int N2 = D.N2, T = D.threads;
 	const int q = N2 / R, total = rows * q;
 	const bool first = (ps == 0);
+	constexpr int GDFT_MAXB = GdftMaxB<R, WIDE>::value;
 	double2 v[GDFT_MAXB][R];
 	int kk[GDFT_MAXB];
 #pragma unroll
@@ -175,6 +189,7 @@ __device__ __forceinline__ void rows_pass(const DftPlan &D, const double2 *__res
 	__syncthreads();
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(512, 1)
 dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__restrict__ st, int64_t stream0)
 {
@@ -192,11 +207,12 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 	for (int ps = 0; ps < D.np2; ps++) {
 		const int R = D.rad2[ps];
 		switch (R) {
-		case 8: rows_pass<8>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
-		case 5: rows_pass<5>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
-		case 4: rows_pass<4>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
-		case 3: rows_pass<3>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
-		default: rows_pass<2>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 10: if constexpr (WIDE) rows_pass<10, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 8: rows_pass<8, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 5: rows_pass<5, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 4: rows_pass<4, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		case 3: rows_pass<3, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
+		default: rows_pass<2, WIDE>(D, Ys, buf, k1a, k1b, rows, ps, Ns); break;
 		}
 		Ns *= R;
 	}
@@ -229,20 +245,36 @@ dft_rows_kernel(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* radix list of a 5-smooth length: 5s, 3s, then the power of two as 8s with a 4 4 / 4 / 2 remainder */
+/* radix list of a 5-smooth length: 10s (a 5 with a 2, prime-factor butterfly), the remaining 5s, 3s, then the power of
+ * two as 8s with a 4 4 / 4 / 2 remainder */
 static bool radix_list(int len, int *rad, int *np)
 {
-	int k = 0, two = 0;
-	while (len % 5 == 0) { rad[k++] = 5; len /= 5; if (k >= DFT_MAX_PASSES) return false; }
-	while (len % 3 == 0) { rad[k++] = 3; len /= 3; if (k >= DFT_MAX_PASSES) return false; }
+	int k = 0, two = 0, five = 0, three = 0;
+	while (len % 5 == 0) { five++; len /= 5; }
+	while (len % 3 == 0) { three++; len /= 3; }
 	while (len % 2 == 0) { two++; len /= 2; }
 	if (len != 1)
 		return false;
-	while (two >= 3 && two != 4) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 8; two -= 3; }
-	while (two >= 2) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 4; two -= 2; }
-	if (two == 1) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = 2; }
+	auto push = [&](int r) { if (k >= DFT_MAX_PASSES) return false; rad[k++] = r; return true; };
+	while (five > 0 && two > 0) { if (!push(10)) return false; five--; two--; }
+	while (five > 0) { if (!push(5)) return false; five--; }
+	while (three > 0) { if (!push(3)) return false; three--; }
+	while (two >= 3 && two != 4) { if (!push(8)) return false; two -= 3; }
+	while (two >= 2) { if (!push(4)) return false; two -= 2; }
+	if (two == 1 && !push(2)) return false;
 	*np = k;
 	return true;
+}
+
+/* points per thread the planner lets a pass of radix r hold (at most GdftMaxB<r> butterflies).  Power-of-two lengths
+ * keep two butterflies per thread in every pass - their plans were tuned that way (n = 2^22: 60 ms per 1024 streams
+ * against 76 ms with the wider tiles) - the mixed lengths use the full GDFT_PTS / 16 points, which at n = 10^7
+ * turns the 2500 x 2000 split with single-column tiles into 2000 x 2500 with 4 columns (64-byte runs of Y) */
+static int pts_of_radix(int r, bool pow2)
+{
+	if (pow2)
+		return 2 * r;
+	return (r == 8 || r == 4 || r == 2) ? 16 : (GDFT_PTS / r) * r;	/* GdftMaxB<r, true> */
 }
 
 bool dft_make_plan(long long n, DftPlan *D)
@@ -251,8 +283,8 @@ bool dft_make_plan(long long n, DftPlan *D)
 		return false;
 	const long long N = n / 2;
 	/*
-	 * Every pass keeps its butterflies in registers, at most GDFT_MAXB per thread: with T threads,
-	 * rows: 2 N2 / R <= MAXB T, columns: CW N1 / R <= MAXB T for every radix R of the list.  Among the
+	 * Every pass keeps its butterflies in registers, at most GDFT_PTS (16 for radix 8/4/2) points per thread:
+	 * with T threads, rows: 2 N2 <= pts T, columns: CW N1 <= pts T for every radix of the list.  Among the
 	 * feasible splits take the widest column tile (coalesced Y stores), then 256 threads (two CTAs per
 	 * SM), then the longest rows.
 	 */
@@ -268,15 +300,16 @@ bool dft_make_plan(long long n, DftPlan *D)
 			int r1[DFT_MAX_PASSES], r2[DFT_MAX_PASSES], k1, k2;
 			if (!radix_list((int) n1, r1, &k1) || !radix_list((int) n2, r2, &k2))
 				continue;
-			int min1 = 8, min2 = 8;
-			for (int i = 0; i < k1; i++) min1 = r1[i] < min1 ? r1[i] : min1;
-			for (int i = 0; i < k2; i++) min2 = r2[i] < min2 ? r2[i] : min2;
-			if (2 * (n2 / min2) > (long long) GDFT_MAXB * T)
+			int pts1 = GDFT_PTS, pts2 = GDFT_PTS;		/* the tightest pass decides */
+			const bool pow2 = (N & (N - 1)) == 0;
+			for (int i = 0; i < k1; i++) pts1 = pts_of_radix(r1[i], pow2) < pts1 ? pts_of_radix(r1[i], pow2) : pts1;
+			for (int i = 0; i < k2; i++) pts2 = pts_of_radix(r2[i], pow2) < pts2 ? pts_of_radix(r2[i], pow2) : pts2;
+			if (2 * n2 > (long long) pts2 * T)
 				continue;
 			if ((size_t) 2 * n2 * sizeof(double2) > 200 * 1024)
 				continue;
 			int cw = 16;
-			while (cw >= 1 && (n2 % cw != 0 || (long long) cw * (n1 / min1) > (long long) GDFT_MAXB * T ||
+			while (cw >= 1 && (n2 % cw != 0 || (long long) cw * n1 > (long long) pts1 * T ||
 					   (size_t) n1 * cw * sizeof(double2) > 200 * 1024))
 				cw >>= 1;
 			if (cw < 1)
@@ -309,16 +342,25 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 	const size_t smem1 = (size_t) D.N1 * D.cw * sizeof(double2);
 	const size_t smem2 = (size_t) 2 * D.N2 * sizeof(double2);
 	cudaError_t e;
-	e = cudaFuncSetAttribute(dft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
+	const bool wide = (((int64_t) D.N1 * D.N2) & ((int64_t) D.N1 * D.N2 - 1)) != 0;	/* not a power of two: dft_make_plan */
+	e = cudaFuncSetAttribute(wide ? dft_cols_kernel<true> : dft_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				 (int) smem1);
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(dft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
+	e = cudaFuncSetAttribute(wide ? dft_rows_kernel<true> : dft_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				 (int) smem2);
 	if (e != cudaSuccess) return e;
 	for (int64_t s0 = 0; s0 < L.nstreams; s0 += work_streams) {
 		const int64_t cs = (L.nstreams - s0 < work_streams) ? L.nstreams - s0 : work_streams;
 		dim3 g1((unsigned) cs, (unsigned) (D.N2 / D.cw));
-		dft_cols_kernel<<<g1, D.threads, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		if (wide)
+			dft_cols_kernel<true><<<g1, D.threads, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
+		else
+			dft_cols_kernel<false><<<g1, D.threads, smem1, L.stream>>>(P, D, L.d_in, d_work, s0);
 		dim3 g2((unsigned) cs, (unsigned) (D.N1 / 2 + 1));
-		dft_rows_kernel<<<g2, D.threads, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		if (wide)
+			dft_rows_kernel<true><<<g2, D.threads, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
+		else
+			dft_rows_kernel<false><<<g2, D.threads, smem2, L.stream>>>(P, D, d_work, L.d_st, s0);
 	}
 	return cudaGetLastError();
 }
