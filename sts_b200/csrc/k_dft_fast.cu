@@ -45,7 +45,13 @@
 #endif
 #define QN1 256
 #define QN2 2048
-#define QCW 16				/* columns per CTA in the column pass */
+#ifndef QCW
+#define QCW 8				/* columns per CTA in the column pass (16 threads per column): 128-thread CTAs, four per SM.  Measured DFT group / pipelined batch per 1024 streams: QCW 16 4.45 / 9.84 ms, 8 4.25 / 9.35 ms, 4 4.73 / 9.85 ms */
+#endif
+#ifndef QCOLS_MINCTA
+#define QCOLS_MINCTA (DFT_MINCTA * 16 / QCW)
+#endif
+#define QCOLS_BOUNDS __launch_bounds__(16 * QCW, QCOLS_MINCTA)
 #define QROW (QN2 + QN2 / 16)		/* padded row: one spare element per 16 */
 
 __device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
@@ -100,15 +106,15 @@ __device__ __forceinline__ double2 cmul_w16(double2 x, int r)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void DFT_BOUNDS
+__global__ void QCOLS_BOUNDS
 dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
 {
-	extern __shared__ double2 buf[];			/* [256][16] */
-	const int c = threadIdx.x & 15, t = threadIdx.x >> 4;	/* t < 16 */
+	extern __shared__ double2 buf[];			/* [256][QCW] */
+	const int c = threadIdx.x % QCW, t = threadIdx.x / QCW;	/* t < 16 */
 	const int j2 = blockIdx.y * QCW + c;
-	const uint32_t *__restrict__ w = in + (stream0 + blockIdx.x) * P.pitch_words + blockIdx.y;
+	const uint32_t *__restrict__ w = in + (stream0 + blockIdx.x) * P.pitch_words + ((2 * j2) >> 5);
 	double2 *__restrict__ Ys = Y + (int64_t) blockIdx.x * ((int64_t) QN1 * QN2);
-	const int sh = 30 - 2 * c;
+	const int sh = 30 - ((2 * j2) & 31);
 	double2 v[16];
 
 	/* pass 0 (Ns = 1): z[2048 j1 + j2] straight from the packed bits, j1 = t + 16 r */
@@ -315,7 +321,7 @@ cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPla
 		cudaStream_t st = (two && which) ? L.stream2 : L.stream;
 		double2 *wk = d_work + (size_t) which * work_streams * ((size_t) QN1 * QN2);
 		dim3 g1((unsigned) cs, QN2 / QCW);
-		dft_cols16<<<g1, 256, smem1, st>>>(P, D, L.d_in, wk, s0);
+		dft_cols16<<<g1, 16 * QCW, smem1, st>>>(P, D, L.d_in, wk, s0);
 		dim3 g2((unsigned) cs, QN1 / 2 + 1);
 		dft_rows16<<<g2, 256, smem2, st>>>(P, D, wk, L.d_st, s0);
 	}
