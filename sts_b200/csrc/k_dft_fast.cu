@@ -35,10 +35,17 @@
 #ifndef DFT_MINCTA
 #define DFT_MINCTA 2
 #endif
-#ifdef DFT_NO_BOUNDS
-#define DFT_BOUNDS
-#else
+/*
+ * The row pass carries no __launch_bounds__: its register count is set by -maxrregcount=$(DFT_MAXREG) in the Makefile
+ * (nvcc ignores that flag for kernels with launch bounds).  It compiles without spills down to 80 registers; fewer
+ * registers make the DFT alone slower but leave room for the other kernels' CTAs beside it.  Measured per 1024
+ * streams, DFT group alone / pipelined batch: 114 registers 4.26 / 9.26 ms, 104: 4.29 / 9.23, 96: 4.32 / 9.20,
+ * 88: 4.33 / 9.13, 80 (three CTAs per SM): 4.74 / 9.07.  -DDFT_ROWS_BOUNDS restores the bounds.
+ */
+#ifdef DFT_ROWS_BOUNDS
 #define DFT_BOUNDS __launch_bounds__(256, DFT_MINCTA)
+#else
+#define DFT_BOUNDS
 #endif
 #ifndef DFT_NO_TW_POWERS
 #define DFT_TW_POWERS 1	/* fewer table lookups: r = 1, 2, 4, 8 loaded, the other twiddle powers by products */
