@@ -457,7 +457,11 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			CKC(cudaEventCreate(&S.k_ev1[k]), "cudaEventCreate");
 		}
 	}
-	CKC(cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking), "cudaStreamCreate");
+	{	/* collectives run at the highest priority: the gather's NCCL kernel must not queue behind the CTAs of the next batch */
+		int pr_lo = 0, pr_hi = 0;
+		cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+		CKC(cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, pr_hi), "cudaStreamCreate");
+	}
 	if (!tmpl.empty())
 		CKC(upload(&ctx->d_templates, tmpl.data(), tmpl.size()), "upload(templates)");
 	if (en & (1u << STSGPU_TEST_LINEARCOMPLEXITY)) {
