@@ -416,3 +416,37 @@ def test_ascii_input_short_text_and_bad_characters(sts, oracle):
     eng.wait()
     assert eng.ascii_status() == (1, -1)
     eng.close()
+
+
+def test_contexts_are_independent_and_release_their_memory(sts, oracle):
+    """two contexts with different parameters side by side give the results each gives alone, and creating /
+    destroying contexts (DFT work buffers, ASCII staging, tallies included) returns the device memory"""
+    import torch
+    raw = oracle.lcg_bytes(0, 2)
+    with sts.Engine(max_streams=2) as a, sts.Engine(max_streams=2, n=1 << 19, linear_complexity_M=1500,
+                                                     test_mask=(1 << 7) | (1 << 15) | (1 << 1)) as b:
+        a.submit(raw, 2, 0)
+        b.submit(raw, 2, 0)                       # reads the first 2 x 2^19 bits
+        b.wait()
+        a.wait()
+        pa, sa, wa = a.results()
+        pb, sb, _ = b.results()
+    with sts.Engine(max_streams=2) as a:
+        pa1, sa1, wa1 = a.run(raw, 2, 0)
+    assert (pa == pa1).all() and (sa == sa1).all() and (wa == wa1).all()
+    with sts.Engine(max_streams=2, n=1 << 19, linear_complexity_M=1500, test_mask=(1 << 7) | (1 << 15) | (1 << 1)) as b:
+        pb1, sb1, _ = b.run(raw, 2, 0)
+    assert (pb == pb1).all() and (sb == sb1).all()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for k in range(6):
+        with sts.Engine(max_streams=64, pipeline_depth=3) as e:
+            e.assess_begin(8)
+            e.generate_lcg(0, 4)
+            e.submit_resident(4, 0)
+            e.wait()
+            e.submit_ascii(np.full(2 << 20, ord("1"), dtype=np.uint8), 1, 0)
+            e.wait()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (64 << 20), "device memory not returned: %d MiB" % ((free0 - free1) >> 20)
