@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
 #include "sts_host.h"
 
 const char *const sts_testNames[STS_NUMOFTESTS + 1] = {	/* parse_args.c:170-187 */
@@ -51,7 +53,7 @@ sts_defaultstate(struct sts_state *s)
 	s->tp.alpha = 0.01;
 	s->runMode = STS_MODE_ITERATE_AND_ASSESS;
 	s->dataFormat = STS_FORMAT_RAW_BINARY;
-	s->numberOfThreads = 1;
+	s->numberOfThreads = 0;			/* 0: not given, min(cores, 16) reader threads (parse_args.c:808-810 takes the cores) */
 	s->batchStreams = 1024;
 	s->workDir = strdup(".");
 }
@@ -317,6 +319,82 @@ sts_iterate(struct sts_thread_state *ts)
 			sts_testDriver[i].iterate(ts);
 }
 
+static double
+now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+/*
+ * One batch is 128 MiB of file (1 GiB of text with -F a): a single fread from the page cache runs at a few GB/s, the
+ * GPU tests 14 GB/s, so the file is read by -T threads (default min(cores, 16)) with pread, each a contiguous slice.
+ * This is the work the reference spreads over its -T iteration threads (utilities.c:1601-1625).
+ */
+struct read_slice {
+	int fd;
+	uint8_t *dst;
+	size_t len;
+	off_t off;
+	ssize_t got;
+	pthread_t tid;
+};
+
+static void *
+read_slice_main(void *arg)
+{
+	struct read_slice *r = arg;
+	size_t done = 0;
+	while (done < r->len) {
+		ssize_t k = pread(r->fd, r->dst + done, r->len - done, r->off + (off_t) done);
+		if (k <= 0)
+			break;
+		done += (size_t) k;
+	}
+	r->got = (ssize_t) done;
+	return NULL;
+}
+
+/* read `len` bytes at `off` of the data file into `dst`; returns the bytes read (short only at end of file) */
+static size_t
+read_parallel(struct sts_state *s, uint8_t *dst, size_t len, off_t off)
+{
+	long nt = s->numberOfThreads;
+	if (nt <= 0) {
+		nt = sysconf(_SC_NPROCESSORS_ONLN);
+		if (nt > 16) nt = 16;
+	}
+	if (nt < 1) nt = 1;
+	if (nt > 64) nt = 64;
+	if (len < ((size_t) 8 << 20))
+		nt = 1;
+	struct read_slice sl[64];
+	const size_t per = ((len / (size_t) nt) + 4095) & ~(size_t) 4095;
+	int used = 0;
+	for (size_t o = 0; o < len; o += per, used++) {
+		sl[used].fd = fileno(s->streamFile);
+		sl[used].dst = dst + o;
+		sl[used].len = (len - o < per) ? len - o : per;
+		sl[used].off = off + (off_t) o;
+		sl[used].got = 0;
+		if (used > 0 && pthread_create(&sl[used].tid, NULL, read_slice_main, &sl[used]) != 0)
+			sts_err(213, __func__, "cannot start a reader thread");
+	}
+	read_slice_main(&sl[0]);
+	size_t total = 0;
+	bool short_seen = false;
+	for (int i = 0; i < used; i++) {
+		if (i > 0)
+			pthread_join(sl[i].tid, NULL);
+		if (!short_seen)
+			total += (size_t) sl[i].got;
+		if ((size_t) sl[i].got < sl[i].len)
+			short_seen = true;
+	}
+	return total;
+}
+
 /*
  * Fill `dst` with `streams` packed streams from the data file.
  * -F r: the file bytes ARE the packed form (utilities.c:1739-1818 + copyBitsToEpsilon :1837-1884).
@@ -400,6 +478,8 @@ sts_invokeTestSuite(struct sts_state *s)
 	}
 	struct sts_thread_state ts = { 0, s, 0, NULL };
 	const long total = s->tp.numOfBitStreams;
+	double t_read = 0.0, t_wait = 0.0, t_keep = 0.0;
+	const double t_begin = now_s();
 	long submitted = 0, done = 0;
 	int w = 0, eof = 0;
 	long waited = 0;				/* batches completed: batch k was read into buf[k % depth] */
@@ -412,6 +492,7 @@ sts_invokeTestSuite(struct sts_state *s)
 			const long want = (total - submitted) < B ? (total - submitted) : B;
 			long have = want;
 			int rc;
+			const double t_r0 = now_s();
 			if (gpu_ascii) {
 				const long off = base_seek + submitted * n;
 				long len = (want + 1) * n;
@@ -423,9 +504,16 @@ sts_invokeTestSuite(struct sts_state *s)
 				window_at_eof[w % depth] = (off + len >= file_size);
 				if (off + len > file_size)
 					len = file_size - off;
-				if (fseek(s->streamFile, off, SEEK_SET) != 0 || (long) fread(buf[w % depth], 1, (size_t) len, s->streamFile) != len)
+				if ((long) read_parallel(s, buf[w % depth], (size_t) len, (off_t) off) != len)
 					sts_err(213, __func__, "cannot read %ld characters at offset %ld of %s", len, off, s->randomDataPath);
 				rc = stsgpu_submit_ascii(s->engine, (const char *) buf[w % depth], len, want, submitted);
+			} else if (!from_stdin && s->dataFormat == STS_FORMAT_RAW_BINARY) {
+				const off_t off = (off_t) base_seek + (off_t) submitted * nb;
+				const size_t got = read_parallel(s, buf[w % depth], (size_t) want * (size_t) nb, off);
+				if (got != (size_t) want * (size_t) nb)		/* utilities.c:1789-1791: a short raw read is fatal */
+					sts_err(213, __func__, "read %zu of %ld streams of %ld bytes from %s: file too short",
+						got / (size_t) nb, want, nb, s->randomDataPath);
+				rc = stsgpu_submit(s->engine, buf[w % depth], have, submitted);
 			} else {
 				have = read_streams(s, buf[w % depth], want);
 				if (have < want)
@@ -436,15 +524,19 @@ sts_invokeTestSuite(struct sts_state *s)
 			}
 			if (rc != STSGPU_OK)
 				sts_err(215, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+			t_read += now_s() - t_r0;
 			batch_want[w % depth] = have;
 			submitted += have;
 			w++;
 		}
 		if (stsgpu_pending(s->engine) == 0)
 			break;
+		const double t_w0 = now_s();
 		int rc = stsgpu_wait(s->engine);
 		if (rc != STSGPU_OK)
 			sts_err(216, __func__, "%s: %s", stsgpu_strerror(rc), stsgpu_last_error(s->engine));
+		const double t_k0 = now_s();
+		t_wait += t_k0 - t_w0;
 		int64_t bn, bf;
 		stsgpu_results(s->engine, &bn, &bf, &s->batch_pvals, NULL, NULL);
 		if (gpu_ascii) {
@@ -474,6 +566,12 @@ sts_invokeTestSuite(struct sts_state *s)
 				printf("Completed %ld iterations of %ld\n", done + k + 1, s->tp.numOfBitStreams);
 		}
 		done += (long) bn;
+		t_keep += now_s() - t_k0;
+	}
+	if (s->debuglevel > 0) {
+		const double dt = now_s() - t_begin;
+		printf("iterate phase: %ld streams of %ld bits in %.3f s = %.2f Gbit/s (read + submit %.3f s, waiting for the GPU %.3f s, "
+		       "record keeping %.3f s)\n", done, n, dt, (double) done * (double) n / dt / 1e9, t_read, t_wait, t_keep);
 	}
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
 	for (int i = 0; i < depth; i++)

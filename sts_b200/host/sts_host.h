@@ -58,7 +58,7 @@ struct sts_state {
 	long jobnum;				/* -j */
 	enum sts_run_mode runMode;		/* -m */
 	enum sts_format dataFormat;		/* -F */
-	long numberOfThreads;			/* -T: accepted; sizes the host packing threads only */
+	long numberOfThreads;			/* -T: threads that read the data file (0 = not given: min(cores, 16)) */
 	long batchStreams;			/* engine batch capacity (new: -B, default 1024) */
 	int device;				/* CUDA device ordinal (new: -D, default 0) */
 	long reportCycle;			/* -I */
