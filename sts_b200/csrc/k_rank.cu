@@ -21,6 +21,7 @@
  *
  * Algorithmic bytes: n/8 per stream (each word is read exactly once).
  */
+#include <stdlib.h>
 #include "common.cuh"
 
 #define RANK_THREADS 128
@@ -68,16 +69,27 @@ __device__ __forceinline__ int nist_rank32_regs(uint32_t (&row)[32])
 	return rank;
 }
 
+/*
+ * Grid-stride over the (stream, 128-matrix group) work items: the kernel is bound by the integer ALU pipe, which a
+ * few warps per scheduler already saturate, so it is launched as a resident grid of STSGPU_RANK_BG CTAs per SM
+ * instead of one CTA per item - the registers a full-occupancy grid would hold are what the FFT and
+ * LinearComplexity CTAs on the same SM need ("register file").  Pipelined batch per 1024 streams: one CTA
+ * per item 9.17 - 9.29 ms, 2 CTAs per SM 9.08, 3: 9.09 - 9.12, 4: 9.16 - 9.18, 6: 9.15 (the kernel alone: 0.52 ms at full
+ * occupancy, 1.0 ms with 3 CTAs per SM).
+ */
 __global__ void __launch_bounds__(RANK_THREADS)
-rank_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st)
+rank_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st, int64_t nstreams, int groups_per_stream)
 {
 	__shared__ uint32_t tile[RANK_THREADS * 33];
 	__shared__ unsigned int f[2];
-	const int64_t s = blockIdx.x;
 	const int tid = threadIdx.x;
+	for (int64_t item = blockIdx.x; item < nstreams * groups_per_stream; item += gridDim.x) {
+	const int64_t s = item / groups_per_stream;
+	const int by = (int) (item - s * groups_per_stream);
+	__syncthreads();					/* tile[] and f[] of the previous item are done with */
 	if (tid < 2)
 		f[tid] = 0;
-	const int64_t m0 = (int64_t) blockIdx.y * RANK_THREADS;		/* first matrix of this CTA */
+	const int64_t m0 = (int64_t) by * RANK_THREADS;			/* first matrix of this item */
 	const int nm = (int) min((int64_t) RANK_THREADS, P.rank_count - m0);
 	const uint4 *__restrict__ src = (const uint4 *) (in + s * P.pitch_words + m0 * 32);
 #pragma unroll
@@ -112,13 +124,20 @@ rank_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 		if (f[1]) atomicAdd(&o[1], (unsigned long long) f[1]);
 		/* F_remaining = matrix_count - F_32 - F_31 is filled by the tail kernel */
 	}
+	}
 }
 
 cudaError_t launch_rank(const DevParams &P, const LaunchCtx &L)
 {
 	if (!(P.enabled & (1u << STSGPU_TEST_RANK)) || P.rank_count < 1)
 		return cudaSuccess;
-	dim3 grid((unsigned) L.nstreams, (unsigned) ((P.rank_count + RANK_THREADS - 1) / RANK_THREADS));
-	rank_kernel<<<grid, RANK_THREADS, 0, L.stream>>>(P, L.d_in, L.d_st);
+	const int gy = (int) ((P.rank_count + RANK_THREADS - 1) / RANK_THREADS);
+	const int64_t items = L.nstreams * gy;
+	static int bg = -1;
+	if (bg < 0)
+		bg = getenv("STSGPU_RANK_BG") ? atoi(getenv("STSGPU_RANK_BG")) : 3;
+	int64_t ctas = bg > 0 ? (int64_t) bg * L.num_sms : items;
+	if (ctas > items) ctas = items;
+	rank_kernel<<<(unsigned) ctas, RANK_THREADS, 0, L.stream>>>(P, L.d_in, L.d_st, L.nstreams, gy);
 	return cudaGetLastError();
 }
