@@ -151,7 +151,7 @@ void stsgpu_destroy(stsgpu_ctx *ctx);
 int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out);
 /*
  * 1 if the engine's FFT can take streams of n bits: n/2 must split into two 5-smooth factors small
- * enough for its register-resident passes (every power of two up to 2^23, 10^6, 10^7 ...).  The reference's libfftw3 plan
+ * enough for its register-resident passes (every power of two up to 2^25, 10^6, 10^7 ...).  The reference's libfftw3 plan
  * (discreteFourierTransform.c:194) takes any n; for other n stsgpu_create refuses the DFT test
  * with STSGPU_E_UNSUPPORTED unless bit 7 of test_mask is clear - never a CPU fallback.
  */

@@ -8,7 +8,8 @@
  *   d_apen_hist B x 3 * 2^apen_m  uint32, the two ApEn histograms in index order
  *   d_dft_work  chunk x n/2       double2, the four-step FFT intermediate (8 MiB per stream)
  * and once per context: templates, LC class LUT, log2 table (Universal), FFT twiddles.
- * `pipeline_depth` slots (default 1) are used round robin so that consecutive batches overlap.
+ * `pipeline_depth` slots (default 1; the host driver and bench.py use 3) are used round robin so that consecutive
+ * batches overlap.  "-F a" batches add a text staging buffer per slot, allocated on first use (k_ascii.cu).
  */
 #include <stdio.h>
 #include <stdlib.h>
