@@ -189,7 +189,8 @@ record_test(struct sts_thread_state *ts, int t)
 				s->success[t]++;
 			}
 		}
-		pv_append(&s->p_val[t], p_value);
+		if (s->runMode == STS_MODE_ITERATE_ONLY || s->resultstxtFlag)
+			pv_append(&s->p_val[t], p_value);	/* -m b without -s: the GPU tallies are the assessment, nothing else reads them */
 	}
 	if (ts->mutex != NULL)
 		pthread_mutex_unlock(ts->mutex);
@@ -455,13 +456,14 @@ sts_invokeTestSuite(struct sts_state *s)
 	const long n = s->tp.n;
 	const long nb = n / 8;
 	const long B = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
-	const bool from_stdin = (strcmp(s->randomDataPath, "-") == 0);
-	const bool gpu_ascii = (s->dataFormat == STS_FORMAT_ASCII_01) && !from_stdin;
-	s->streamFile = from_stdin ? stdin : fopen(s->randomDataPath, "rb");
-	if (s->streamFile == NULL)
+	const bool generated = (s->generator == 1);
+	const bool from_stdin = !generated && (strcmp(s->randomDataPath, "-") == 0);
+	const bool gpu_ascii = !generated && (s->dataFormat == STS_FORMAT_ASCII_01) && !from_stdin;
+	s->streamFile = generated ? NULL : (from_stdin ? stdin : fopen(s->randomDataPath, "rb"));
+	if (s->streamFile == NULL && !generated)
 		sts_err(210, __func__, "cannot open data file %s: %s", s->randomDataPath, strerror(errno));
 	long base_seek = 0, file_size = 0;
-	if (!from_stdin) {
+	if (!from_stdin && !generated) {
 		const long per_stream = (s->dataFormat == STS_FORMAT_RAW_BINARY) ? nb : n;
 		base_seek = s->jobnum * per_stream * s->tp.numOfBitStreams;
 		if (fseek(s->streamFile, 0, SEEK_END) != 0 || (file_size = ftell(s->streamFile)) < 0 ||
@@ -469,9 +471,10 @@ sts_invokeTestSuite(struct sts_state *s)
 			sts_err(211, __func__, "cannot seek to job %ld in %s", s->jobnum, s->randomDataPath);
 	}
 	const size_t buf_bytes = gpu_ascii ? (size_t) (B + 1) * (size_t) n : (size_t) B * (size_t) nb;
-	const int depth = gpu_ascii ? 2 : STS_PIPELINE_DEPTH;	/* text is 8 bytes per tested byte: PCIe bound at any depth */
-	uint8_t *buf[STS_PIPELINE_DEPTH];
-	for (int i = 0; i < depth; i++) {
+	/* text is 8 bytes per tested byte: PCIe bound at any depth; generated input is resident: two suffice */
+	const int depth = (gpu_ascii || generated) ? 2 : STS_PIPELINE_DEPTH;
+	uint8_t *buf[STS_PIPELINE_DEPTH] = { NULL };
+	for (int i = 0; i < depth && !generated; i++) {
 		buf[i] = stsgpu_host_alloc(buf_bytes);
 		if (buf[i] == NULL)
 			sts_err(212, __func__, "cannot allocate pinned read buffer of %zu bytes", buf_bytes);
@@ -493,7 +496,13 @@ sts_invokeTestSuite(struct sts_state *s)
 			long have = want;
 			int rc;
 			const double t_r0 = now_s();
-			if (gpu_ascii) {
+			if (generated) {
+				/* job `jobnum` of the reference's distributed mode would read streams [jobnum * iterations, ...) of
+				 * the generator's file: skip ahead to the same place */
+				rc = stsgpu_generate_lcg(s->engine, s->jobnum * total + submitted, want);
+				if (rc == STSGPU_OK)
+					rc = stsgpu_submit_resident(s->engine, want, submitted);
+			} else if (gpu_ascii) {
 				const long off = base_seek + submitted * n;
 				long len = (want + 1) * n;
 				if (off >= file_size) {
@@ -576,7 +585,7 @@ sts_invokeTestSuite(struct sts_state *s)
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
 	for (int i = 0; i < depth; i++)
 		stsgpu_host_free(buf[i]);
-	if (!from_stdin)
+	if (!from_stdin && !generated)
 		fclose(s->streamFile);
 	s->streamFile = NULL;
 }

@@ -61,6 +61,7 @@ struct sts_state {
 	long numberOfThreads;			/* -T: threads that read the data file (0 = not given: min(cores, 16)) */
 	long batchStreams;			/* engine batch capacity (new: -B, default 1024) */
 	int device;				/* CUDA device ordinal (new: -D, default 0) */
+	long generator;				/* -g: 0 = data file (the only value sts 3 accepts); 1 = tools/generators.c generator 1 (LCG) made on the GPU */
 	long reportCycle;			/* -I */
 	int debuglevel;				/* -v */
 	bool legacy_output;			/* -O: 10 uniformity bins, finalAnalysisReport.txt (parse_args.c:585, :792-803) */

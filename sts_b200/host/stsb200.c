@@ -16,10 +16,11 @@
 static const char *usage =
 	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
 	"               [-I reportCycle] [-O] [-s] [-w workDir] [-F r|a] [-j jobnum] [-m b|i|a] [-d pvaluesdir] [-T threads]\n"
-	"               [-B batch] [-D device] [datafile | -]\n"
+	"               [-B batch] [-D device] [-g 0|1] [datafile | -]\n"
 	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
-	"  -m b and -m i both iterate on the GPU and write workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b also writes the\n"
-	"  reference's result.txt (with -O the table of its legacy finalAnalysisReport.txt), tallied on the GPU;\n"
+	"  -m i iterates on the GPU and writes workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b iterates and writes the\n"
+	"  reference's result.txt (with -O the table of its legacy finalAnalysisReport.txt) from tallies kept on the GPU,\n"
+	"  without keeping the p-values; -g 1 tests the linear congruential generator of tools/generators, made on the GPU;\n"
 	"  -m a -d dir assesses the .pvalues files of earlier -m i runs, streamed through the GPU tallies in bounded memory.\n";
 
 int
@@ -29,7 +30,7 @@ main(int argc, char **argv)
 	sts_defaultstate(&st);
 	int opt;
 	char *brkt, *phrase;
-	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:d:Osh")) != -1) {
+	while ((opt = getopt(argc, argv, "v:t:P:S:i:I:w:F:j:m:T:B:D:d:g:Osh")) != -1) {
 		switch (opt) {
 		case 'v': st.debuglevel = atoi(optarg); break;
 		case 't':
@@ -78,6 +79,11 @@ main(int argc, char **argv)
 			else sts_err(1, __func__, "-m mode: %s must be b, i or a", optarg);
 			break;
 		case 'd': free(st.pvalues_dir); st.pvalues_dir = strdup(optarg); break;
+		case 'g':	/* sts 3 only accepts -g 0 (parse_args.c:480-483); generator 1 of tools/generators.c runs on the GPU here */
+			st.generator = atol(optarg);
+			if (st.generator != 0 && st.generator != 1)
+				sts_err(1, __func__, "-g generator: %ld must be 0 (data file) or 1 (linear congruential, made on the GPU)", st.generator);
+			break;
 		case 'T': st.numberOfThreads = atol(optarg); break;
 		case 'B': st.batchStreams = atol(optarg); break;
 		case 'D': st.device = atoi(optarg); break;
@@ -91,6 +97,8 @@ main(int argc, char **argv)
 	}
 	if (optind == argc - 1)
 		st.randomDataPath = strdup(argv[optind]);
+	else if (optind == argc && st.generator == 1)
+		st.randomDataPath = strdup("((tools/generators 1, linear congruential, generated on the GPU))");
 	else if (optind != argc || st.runMode != STS_MODE_ASSESS_ONLY) {	/* parse_args.c:706-732: -m a needs no data file */
 		fputs(usage, stderr);
 		return 1;
@@ -116,14 +124,16 @@ main(int argc, char **argv)
 	sts_init(&st);
 	sts_invokeTestSuite(&st);
 	sts_print(&st);				/* -s */
-	sts_write_p_val_to_file(&st);
+	if (st.runMode == STS_MODE_ITERATE_ONLY)	/* sts.c:358-360 */
+		sts_write_p_val_to_file(&st);
 	sts_metrics(&st);			/* -m b: result.txt (or, with -O, the legacy table), tallied on the GPU */
 	if (st.debuglevel > 0) {
 		for (int t = 1; t <= STS_NUMOFTESTS; t++)
 			if (st.testVector[t])
 				printf("%-26s count %8ld valid %8ld success %8ld failure %8ld\n", sts_testNames[t], st.count[t],
 				       st.valid[t], st.success[t], st.failure[t]);
-		printf("wrote %s/sts.%04ld.%ld.%ld.pvalues\n", st.workDir, st.jobnum, st.tp.numOfBitStreams, st.tp.n);
+		if (st.runMode == STS_MODE_ITERATE_ONLY)
+			printf("wrote %s/sts.%04ld.%ld.%ld.pvalues\n", st.workDir, st.jobnum, st.tp.numOfBitStreams, st.tp.n);
 	}
 	sts_destroy(&st);
 	return 0;

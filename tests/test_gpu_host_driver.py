@@ -224,3 +224,28 @@ def test_dash_s_results_and_data_files_identical_to_reference(lcg8, tmp_path):
                 assert open(mine).read() == open(os.path.join(root, f)).read(), rel
                 seen += 1
     assert seen == 15 + 1 + 148 + 1 + 18 + 1       # results.txt x 15, cusum, templates, excursions, variant, serial
+
+
+def test_generator_1_on_the_device(tmp_path, oracle):
+    """-g 1: the linear congruential generator of tools/generators made on the GPU (skip-ahead) is the file the
+    generator writes - same p-values as the golden file run, -j jobs start at their own streams, and -m b keeps no
+    p-values yet writes the same result.txt as a run on the file"""
+    g = load_golden("lcg_default_8")
+    w = str(tmp_path / "gen")
+    run([STSB200, "-g", "1", "-m", "i", "-i", "8", "-B", "3", "-w", w])
+    pv = read_pvalues(os.path.join(w, "sts.0000.8.1048576.pvalues"))
+    for t in range(1, 16):
+        ref = g["pv_%d" % t]
+        assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9, "test %d" % t
+    wj = str(tmp_path / "genj")
+    run([STSB200, "-g", "1", "-m", "i", "-j", "1", "-i", "4", "-t", "1,7,15", "-w", wj])
+    pj = read_pvalues(os.path.join(wj, "sts.0001.4.1048576.pvalues"))
+    for t in (1, 7, 15):
+        ref = g["pv_%d" % t][4:]
+        assert rel_err(pj[t].reshape(ref.shape), ref).max() <= 1e-9
+    p = str(tmp_path / "lcg32.bin")
+    oracle.lcg_bytes(0, 32).tofile(p)
+    run([STSB200, "-m", "b", "-i", "32", "-F", "r", "-w", str(tmp_path / "file"), p])
+    run([STSB200, "-g", "1", "-m", "b", "-i", "32", "-B", "7", "-w", str(tmp_path / "made")])
+    assert result_body(str(tmp_path / "file" / "result.txt")) == result_body(str(tmp_path / "made" / "result.txt"))
+    assert not [f for f in os.listdir(str(tmp_path / "made")) if f.endswith(".pvalues")]     # sts.c:358: only -m i writes them

@@ -28,6 +28,7 @@ def run(args, **kw):
     (["-P", "12=3", "f"], "-P num=value"),
     (["-i", "0", "f"], "-i iterations"),
     (["-m", "a"], "-m a requires -d"),
+    (["-g", "2"], "-g generator"),
 ])
 def test_argument_errors_exit_1_with_the_flag_named(args, needle):
     r = run(args)
