@@ -10,7 +10,35 @@ GOLDEN_DIR = os.path.join(HERE, "golden")
 
 def golden_cases():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [x for x in names if not x.startswith("assess_")]	# assess_*: assessment reports, see make_assess_golden.py
+    # assess_*: assessment reports (make_assess_golden.py); ascii_*: -F a readings (make_ascii_golden.py)
+    return [x for x in names if not x.startswith(("assess_", "ascii_"))]
+
+
+def ascii_lines(bits, line):
+    """the bits as '0' / '1' characters (uint8) with a line break after every `line` digits, and one at the end"""
+    ch = (np.asarray(bits, dtype=np.uint8) + ord("0")).astype(np.uint8)
+    rows = -(-ch.size // line)
+    out = np.full((rows, line + 1), ord("\n"), dtype=np.uint8)
+    flat = np.full(rows * line, ord(" "), dtype=np.uint8)
+    flat[:ch.size] = ch
+    out[:, :line] = flat.reshape(rows, line)
+    return out.reshape(-1)
+
+
+def ascii_seek_rule_streams(text, n, streams):
+    """parseBitsASCIIInput (utilities.c:1682-1697): iteration k = the first n digits at or after character k n,
+    packed MSB first; returns (packed [streams][n / 8], number of complete streams)"""
+    text = np.asarray(text, dtype=np.uint8)
+    out = np.zeros((streams, n // 8), dtype=np.uint8)
+    complete = 0
+    for k in range(streams):
+        w = text[k * n:]
+        d = w[(w == ord("0")) | (w == ord("1"))][:n] - ord("0")
+        if d.size < n:
+            break
+        out[k] = np.packbits(d)
+        complete += 1
+    return out, complete
 
 
 def load_golden(name):

@@ -249,3 +249,19 @@ def test_generator_1_on_the_device(tmp_path, oracle):
     run([STSB200, "-g", "1", "-m", "b", "-i", "32", "-B", "7", "-w", str(tmp_path / "made")])
     assert result_body(str(tmp_path / "file" / "result.txt")) == result_body(str(tmp_path / "made" / "result.txt"))
     assert not [f for f in os.listdir(str(tmp_path / "made")) if f.endswith(".pvalues")]     # sts.c:358: only -m i writes them
+
+
+def test_ascii_file_against_committed_reference_reading(tmp_path, oracle):
+    """the same as test_ascii_file_with_line_breaks_matches_reference, but against the committed fixture
+    (tests/golden/ascii_lines80_3.npz, made by the reference binary) so that it also runs where oracle/_ref is absent"""
+    from golden_util import GOLDEN_DIR, ascii_lines
+    g = np.load(os.path.join(GOLDEN_DIR, "ascii_lines80_3.npz"))
+    it = int(g["iterations"])
+    ap = str(tmp_path / "ascii.txt")
+    ascii_lines(np.unpackbits(oracle.lcg_bytes(0, int(g["source_streams"]))), int(g["line"])).tofile(ap)
+    w = str(tmp_path / "w")
+    run([STSB200, "-m", "i", "-i", str(it), "-B", "2", "-F", "a", "-w", w, ap])
+    pv = read_pvalues(os.path.join(w, "sts.0000.%d.1048576.pvalues" % it))
+    for t in range(1, 16):
+        ref = g["pv_%d" % t]
+        assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9, "test %d" % t

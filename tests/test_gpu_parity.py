@@ -354,17 +354,10 @@ def ascii_text(bits, line):
 
 
 def seek_rule_streams(text, n, streams):
-    """parseBitsASCIIInput (utilities.c:1682-1697): iteration k = the first n digits at or after character k n"""
-    out = np.zeros((streams, n // 8), dtype=np.uint8)
-    complete = 0
-    for k in range(streams):
-        w = text[k * n:]
-        d = w[(w == ord("0")) | (w == ord("1"))][:n] - ord("0")
-        if d.size < n:
-            break
-        out[k] = np.packbits(d)
-        complete += 1
-    return out, complete
+    """the reference's reading of an ASCII file, pinned to the reference binary by
+    tests/test_oracle_golden.py::test_ascii_seek_rule_against_reference_reading"""
+    from golden_util import ascii_seek_rule_streams
+    return ascii_seek_rule_streams(text, n, streams)
 
 
 @pytest.mark.parametrize("line", [0, 64, 61, 1])

@@ -72,3 +72,25 @@ def test_oracle_assessment_against_reference_report(oracle):
     e = [c for t in (12, 13) for c in range(lay.pv_off[t], lay.pv_off[t] + lay.pv_cnt[t])]
     assert (f["freq"] == 1).all() and np.allclose(f["uniformity"], 1.0) and (f["passed"] == 10).all()
     assert len(e) == 26
+
+
+def test_ascii_seek_rule_against_reference_reading(oracle):
+    """-F a: the reference seeks to character iteration * n and reads n digits skipping white space
+    (utilities.c:1682-1697).  tests/golden/ascii_lines80_3.npz holds its p-values for a text with a line break every
+    80 digits; the numpy statement of that rule (golden_util.ascii_seek_rule_streams, which the GPU tests use as the
+    expected packing) fed to the oracle must reproduce them bit for bit - a sequential reader would not."""
+    import os
+    from golden_util import GOLDEN_DIR, ascii_lines, ascii_seek_rule_streams
+    g = np.load(os.path.join(GOLDEN_DIR, "ascii_lines80_3.npz"))
+    n, it = int(g["n"]), int(g["iterations"])
+    bits = np.unpackbits(oracle.lcg_bytes(0, int(g["source_streams"])))
+    text = ascii_lines(bits, int(g["line"]))
+    packed, complete = ascii_seek_rule_streams(text, n, it)
+    assert complete == it
+    assert not (packed[1] == np.packbits(bits[n:2 * n])).all()        # the overlap: stream 1 is NOT bits [n, 2n)
+    mask = (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 9) | (1 << 12) | (1 << 13)     # the cheap tests
+    pv, st, w, lay = oracle.run(oracle.make_params(test_mask=mask), packed.reshape(-1), it, nthreads=it)
+    for t in range(1, 16):
+        if (mask >> t) & 1:
+            mine = pv[:, lay.pv_off[t]:lay.pv_off[t] + lay.pv_cnt[t]]
+            assert (mine == g["pv_%d" % t]).all(), "test %d" % t
