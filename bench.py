@@ -9,10 +9,12 @@ larger than L2).  Streams are the reference's own LCG (tools/generators 1), gene
 skip-ahead so that rank r owns streams [r*1024, (r+1)*1024) - the reference's `-j` sharding rule.
 
   value   whole-job Gbit/s with the batch already resident in HBM: kernels + tails + D2H of the
-          records (+ NCCL gather of the p-values to rank 0 when N > 1), max over ranks.
+          records (+ NCCL gather of the p-values to rank 0 when N > 1), max over ranks; two batches in flight.
   e2e     the same metric through the C ABI with HOST input: stsgpu_submit() from pinned host
-          memory (H2D inside), wait, records on the host, gather.
-  roofline  dominant kernel group of the step, CUDA-event timed on its own stream in the timed region.
+          memory (H2D inside), wait, records on the host, gather; three batches in flight.
+  roofline  dominant kernel group of the step (the DFT): algorithmic bytes / its CUDA-event duration with the
+          groups serialised, taken in a short pass right after the timed region on the same inputs; the same
+          events inside the timed region, where batches and streams overlap, are reported as in_region_ms.
   cpu_baseline  the unmodified reference binary (oracle/_ref/sts, built from /root/reference with the
           fftw3 shim) on all host cores, on a bounded sample of the same workload (rank 0, N = 1).
 
