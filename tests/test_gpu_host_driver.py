@@ -265,3 +265,17 @@ def test_ascii_file_against_committed_reference_reading(tmp_path, oracle):
     for t in range(1, 16):
         ref = g["pv_%d" % t]
         assert rel_err(pv[t].reshape(ref.shape), ref).max() <= 1e-9, "test %d" % t
+
+
+def test_reports_against_committed_reference_bodies(tmp_path):
+    """result.txt of a -m b run and of a -m i x 2 jobs + -m a run, on streams made by -g 1, against the bodies the
+    reference binary wrote for the same streams (tests/golden/make_report_golden.py); needs neither oracle/_ref nor
+    a data file"""
+    gold = os.path.join(ROOT, "tests", "golden")
+    run([STSB200, "-g", "1", "-m", "b", "-i", "32", "-B", "13", "-w", str(tmp_path / "b")])
+    assert result_body(str(tmp_path / "b" / "result.txt")) == open(os.path.join(gold, "result_lcg32_body.txt")).read()
+    d = str(tmp_path / "pv")
+    for k in range(2):
+        run([STSB200, "-g", "1", "-m", "i", "-j", str(k), "-i", "4", "-w", d])
+    run([STSB200, "-m", "a", "-d", d, "-i", "8", "-w", str(tmp_path / "a")])
+    assert result_body(str(tmp_path / "a" / "result.txt")) == open(os.path.join(gold, "assess_lcg8_body.txt")).read()
