@@ -150,6 +150,13 @@ int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out);
 void stsgpu_destroy(stsgpu_ctx *ctx);
 int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out);
 /*
+ * The same layout for a parameter set WITHOUT creating an engine and without touching a device: what the 15
+ * X_init() would leave enabled (enabled_mask), and the per-test p-value / statistic counts.  The host uses it to
+ * size state->p_val[] before the first batch; `device` and `pipeline_depth` are ignored.  STSGPU_E_INVAL for
+ * arguments stsgpu_create would refuse, or when no test is left enabled.
+ */
+int stsgpu_query_layout(const stsgpu_params *p, stsgpu_layout *out);
+/*
  * 1 if the engine's FFT can take streams of n bits: n/2 must split into two 5-smooth factors small
  * enough for its register-resident passes (every power of two up to 2^25, 10^6, 10^7 ...).  The reference's libfftw3 plan
  * (discreteFourierTransform.c:194) takes any n; for other n stsgpu_create refuses the DFT test

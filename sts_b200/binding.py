@@ -18,7 +18,7 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
               "RandomExcursions", "RandomExcursionsVariant", "Serial", "LinearComplexity"]
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
-EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_dft_supported", "stsgpu_submit",
+EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_query_layout", "stsgpu_dft_supported", "stsgpu_submit",
            "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
@@ -80,6 +80,7 @@ def load_library():
     lib.stsgpu_destroy.argtypes = [vp]
     lib.stsgpu_destroy.restype = None
     lib.stsgpu_get_layout.argtypes = [vp, C.POINTER(Layout)]
+    lib.stsgpu_query_layout.argtypes = [C.POINTER(Params), C.POINTER(Layout)]
     lib.stsgpu_dft_supported.argtypes = [i64]
     lib.stsgpu_submit.argtypes = [vp, vp, i64, i64]
     lib.stsgpu_submit_resident.argtypes = [vp, i64, i64]
@@ -122,6 +123,16 @@ def load_library():
 def dft_supported(n):
     """can the engine's FFT take streams of n bits (n/2 = two 5-smooth factors <= 3200)"""
     return bool(load_library().stsgpu_dft_supported(n))
+
+
+def query_layout(params=None, **kw):
+    """record layout for a parameter set without an engine or a device (stsgpu_query_layout)"""
+    p = params if params is not None else default_params(**kw)
+    lay = Layout()
+    rc = load_library().stsgpu_query_layout(C.byref(p), C.byref(lay))
+    if rc != 0:
+        raise EngineError("stsgpu_query_layout: %s" % load_library().stsgpu_strerror(rc).decode())
+    return lay
 
 
 def default_params(**kw):

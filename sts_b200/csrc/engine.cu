@@ -227,6 +227,69 @@ static const double univ_expected[17] = { 0, 0, 0, 0, 0, 0, 5.2177052, 6.1962507
 static const double univ_variance[17] = { 0, 0, 0, 0, 0, 0, 2.954, 3.125, 3.238, 3.311, 3.356, 3.384, 3.401, 3.410,
 	3.416, 3.419, 3.421 };							/* universal.c:77-80 */
 
+/*
+ * Record layout for a parameter set (must match oracle_layout_for: same contract, written independently): which
+ * tests survive the X_init() checks, how many p-values and integer statistics each contributes, and the
+ * non-overlapping templates.  Pure host arithmetic - no CUDA call.
+ */
+static void compute_layout(const stsgpu_params *p, stsgpu_layout *out, std::vector<uint32_t> *tmpl)
+{
+	stsgpu_layout &lay = *out;
+	memset(&lay, 0, sizeof(lay));
+	int L = 0;
+	const uint32_t en = effective_mask(p, &L);
+	lay.enabled_mask = en;
+	lay.universal_L = L;
+	const int64_t n = p->n;
+	tmpl->clear();
+	if (en & (1u << STSGPU_TEST_NON_OVERLAPPING))
+		for (uint32_t v = 1; v < (1u << p->non_overlapping_m); v++)
+			if (template_accepted(v, p->non_overlapping_m))
+				tmpl->push_back(v);
+	lay.ntemplates = (int32_t) tmpl->size();
+	lay.nw = lay.ntemplates * 8;
+	const int64_t bfN = p->block_frequency_M > 0 ? n / p->block_frequency_M : 0;
+	const int pvc[16] = { 0, 1, 1, 2, 1, 1, 1, 1, lay.ntemplates, 1, 1, 1, 8, 18, 2, 1 };
+	const int stc[16] = { 0, 1, 1 + (int) bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 49, 19, 3, 7 };
+	for (int t = 1; t <= 15; t++) {
+		if (!((en >> t) & 1u))
+			continue;
+		lay.pv_off[t] = lay.npv; lay.pv_cnt[t] = pvc[t]; lay.npv += pvc[t];
+		lay.st_off[t] = lay.nst; lay.st_cnt[t] = stc[t]; lay.nst += stc[t];
+	}
+}
+
+/* the argument checks stsgpu_create makes before it touches the device */
+static int check_params(const stsgpu_params *p, const char **why)
+{
+	if (p == NULL || p->abi_version != STSGPU_ABI_VERSION) {
+		*why = "bad params pointer or ABI version";
+		return STSGPU_E_INVAL;
+	}
+	if (p->n < 8 || (p->n % 8) != 0 || p->max_streams < 1) {	/* parse_args.c:939: n must be a multiple of 8 */
+		*why = "n must be a positive multiple of 8 and max_streams >= 1";
+		return STSGPU_E_INVAL;
+	}
+	if (p->n > (1LL << 31) - 4096) {
+		*why = "n above 2^31 bits per stream";
+		return STSGPU_E_UNSUPPORTED;
+	}
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_query_layout(const stsgpu_params *p, stsgpu_layout *out)
+{
+	const char *why = "";
+	if (out == NULL)
+		return STSGPU_E_INVAL;
+	const int rc = check_params(p, &why);
+	if (rc != STSGPU_OK)
+		return rc;
+	std::vector<uint32_t> tmpl;
+	compute_layout(p, out, &tmpl);
+	return out->npv == 0 ? STSGPU_E_INVAL : STSGPU_OK;
+}
+
 static int fail_create(stsgpu_ctx *ctx, int code, const char *msg)
 {
 	snprintf(g_create_err, sizeof(g_create_err), "%s%s%s", msg, ctx && ctx->err[0] ? ": " : "",
@@ -253,12 +316,12 @@ static double2 unit_root(long double num, long double den)	/* exp(-2 pi i num / 
 extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 {
 	g_create_err[0] = 0;
-	if (p == NULL || out == NULL || p->abi_version != STSGPU_ABI_VERSION)
-		return fail_create(NULL, STSGPU_E_INVAL, "bad params pointer or ABI version");
-	if (p->n < 8 || (p->n % 8) != 0 || p->max_streams < 1)		/* parse_args.c:939: n must be a multiple of 8 */
-		return fail_create(NULL, STSGPU_E_INVAL, "n must be a positive multiple of 8 and max_streams >= 1");
-	if (p->n > (1LL << 31) - 4096)
-		return fail_create(NULL, STSGPU_E_UNSUPPORTED, "n above 2^31 bits per stream");
+	{
+		const char *why = "";
+		const int rc = (out == NULL) ? STSGPU_E_INVAL : check_params(p, &why);
+		if (rc != STSGPU_OK)
+			return fail_create(NULL, rc, out == NULL ? "bad output pointer" : why);
+	}
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= p->device || p->device < 0)
 		return fail_create(NULL, STSGPU_E_NO_DEVICE, "no CUDA device with the requested ordinal");
@@ -275,30 +338,14 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	if (cudaSetDevice(p->device) != cudaSuccess)
 		return fail_create(ctx, STSGPU_E_CUDA, "cudaSetDevice failed");
 
-	/* ---- layout (must match oracle_layout_for: same contract, written independently) ---- */
+	/* ---- layout ---- */
 	stsgpu_layout &lay = ctx->lay;
-	memset(&lay, 0, sizeof(lay));
-	int L = 0;
-	const uint32_t en = effective_mask(p, &L);
-	lay.enabled_mask = en;
-	lay.universal_L = L;
-	const int64_t n = p->n;
 	std::vector<uint32_t> tmpl;
-	if (en & (1u << STSGPU_TEST_NON_OVERLAPPING))
-		for (uint32_t v = 1; v < (1u << p->non_overlapping_m); v++)
-			if (template_accepted(v, p->non_overlapping_m))
-				tmpl.push_back(v);
-	lay.ntemplates = (int32_t) tmpl.size();
-	lay.nw = lay.ntemplates * 8;
+	compute_layout(p, &lay, &tmpl);
+	const uint32_t en = lay.enabled_mask;
+	const int L = lay.universal_L;
+	const int64_t n = p->n;
 	const int64_t bfN = p->block_frequency_M > 0 ? n / p->block_frequency_M : 0;
-	const int pvc[16] = { 0, 1, 1, 2, 1, 1, 1, 1, lay.ntemplates, 1, 1, 1, 8, 18, 2, 1 };
-	const int stc[16] = { 0, 1, 1 + (int) bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 49, 19, 3, 7 };
-	for (int t = 1; t <= 15; t++) {
-		if (!((en >> t) & 1u))
-			continue;
-		lay.pv_off[t] = lay.npv; lay.pv_cnt[t] = pvc[t]; lay.npv += pvc[t];
-		lay.st_off[t] = lay.nst; lay.st_cnt[t] = stc[t]; lay.nst += stc[t];
-	}
 	if (lay.npv == 0)
 		return fail_create(ctx, STSGPU_E_INVAL, "no test left enabled for these parameters");
 

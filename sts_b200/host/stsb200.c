@@ -108,6 +108,12 @@ main(int argc, char **argv)
 	if (st.tp.numOfBitStreams < 1)
 		sts_err(1, __func__, "-i iterations: %ld must be > 0", st.tp.numOfBitStreams);
 	st.binsIterations = st.tp.numOfBitStreams;
+	if ((st.tp.n % 8) != 0)				/* parse_args.c:939-947 */
+		sts_err(1, __func__, "bitcount(n): %ld must be a multiple of 8. The added complexity of supporting "
+			"a sequence that starts or ends on a non-byte boundary outweighs the "
+			"convenience of permitting arbitrary bit lengths", st.tp.n);
+	if (st.tp.n < 1000)				/* GLOBAL_MIN_BITCOUNT, defs.h:200 */
+		sts_err(1, __func__, "bitcount(n): %ld must >= %d", st.tp.n, 1000);
 
 	if (st.runMode == STS_MODE_ASSESS_ONLY) {	/* sts.c:352-383: init, read the p-value files, metrics */
 		if (st.pvalues_dir == NULL)

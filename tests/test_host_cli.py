@@ -29,6 +29,9 @@ def run(args, **kw):
     (["-i", "0", "f"], "-i iterations"),
     (["-m", "a"], "-m a requires -d"),
     (["-g", "2"], "-g generator"),
+    (["-S", "992", "f"], "bitcount(n): 992 must >= 1000"),                 # parse_args.c:945-947
+    (["-S", "1001", "f"], "bitcount(n): 1001 must be a multiple of 8"),    # parse_args.c:939-944
+    (["-P", "9=104", "f"], "bitcount(n): 104 must >= 1000"),
 ])
 def test_argument_errors_exit_1_with_the_flag_named(args, needle):
     r = run(args)
