@@ -1,0 +1,377 @@
+/*
+ * cuda_emu_rt.cpp - TEST INFRASTRUCTURE (see cuda_emu.h): the fiber scheduler that steps the threads of a CTA
+ * through barriers and warp collectives, and a synchronous stand-in for the few CUDA runtime calls the engine makes.
+ */
+#include "cuda_emu.h"
+#include <stdio.h>
+#include <time.h>
+#include <sys/mman.h>
+#include <vector>
+#include <thread>
+#include <mutex>
+#include <atomic>
+
+/* void emu_switch(void **save_sp, void *next_sp): save the callee-saved registers, swap stacks, restore */
+asm(R"(
+.text
+.globl emu_switch
+.hidden emu_switch
+.type emu_switch,@function
+emu_switch:
+	pushq %rbp
+	pushq %rbx
+	pushq %r12
+	pushq %r13
+	pushq %r14
+	pushq %r15
+	movq %rsp, (%rdi)
+	movq %rsi, %rsp
+	popq %r15
+	popq %r14
+	popq %r13
+	popq %r12
+	popq %rbx
+	popq %rbp
+	ret
+.size emu_switch,.-emu_switch
+)");
+extern "C" void emu_switch(void **save_sp, void *next_sp);
+
+namespace emu {
+
+enum { RUN = 0, WAIT_BAR = 1, WAIT_WARP = 2, WAIT_DRAIN = 3 };
+static const size_t STACK_BYTES = 256 * 1024;
+static const int MAX_THREADS = 1024;
+static const size_t DYN_SMEM_BYTES = 256 * 1024;
+
+struct Warp {
+	uint64_t val[32];
+	uint32_t alive, arrived, part, mask;
+	int phase, left;			/* phase 0: collecting deposits, 1: participants copy out */
+};
+struct Fiber {
+	void *sp;
+	Ctx ctx;
+	bool done;
+	int wait;
+	unsigned bar_seen;
+};
+struct Block {
+	Fiber fib[MAX_THREADS];
+	Warp warps[MAX_THREADS / 32];
+	int n, alive, bar_arrived;
+	unsigned bar_gen;
+	unsigned long ticks;			/* bumped whenever any fiber makes progress past a wait */
+	void *sched_sp;
+	const std::function<void()> *body;
+	char *stacks;
+	char *smem;
+};
+
+thread_local Ctx *cur = nullptr;
+static thread_local Block *blk = nullptr;
+static thread_local Fiber *curf = nullptr;
+
+static Block *new_block()
+{
+	Block *b = new Block();
+	b->stacks = (char *) mmap(nullptr, STACK_BYTES * MAX_THREADS, PROT_READ | PROT_WRITE,
+				  MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+	if (b->stacks == (char *) MAP_FAILED) {
+		fprintf(stderr, "cuda_emu: cannot map fiber stacks\n");
+		abort();
+	}
+	if (posix_memalign((void **) &b->smem, 1024, DYN_SMEM_BYTES) != 0)
+		abort();
+	return b;
+}
+
+void *dyn_smem() { return blk->smem; }
+
+static inline void yield() { emu_switch(&curf->sp, blk->sched_sp); }
+
+static void warp_try_release(Warp &w)
+{
+	const uint32_t need = w.mask & w.alive;
+	if (w.phase == 0 && w.arrived != 0 && (w.arrived & need) == need) {
+		w.phase = 1;
+		w.part = w.arrived;
+		w.left = __builtin_popcount(w.arrived);
+		blk->ticks++;
+	}
+}
+
+static void fiber_exit()
+{
+	Block *b = blk;
+	Fiber *f = curf;
+	f->done = true;
+	b->alive--;
+	b->ticks++;
+	Warp &w = *f->ctx.warp;
+	w.alive &= ~(1u << f->ctx.lane);
+	warp_try_release(w);			/* the lanes still waiting no longer wait for this one */
+	if (b->bar_arrived > 0 && b->bar_arrived == b->alive) {	/* an exited thread counts as arrived */
+		b->bar_arrived = 0;
+		b->bar_gen++;
+	}
+	void *dummy;
+	emu_switch(&dummy, b->sched_sp);
+	abort();				/* a finished fiber is never resumed */
+}
+
+static void fiber_entry()
+{
+	(*blk->body)();
+	fiber_exit();
+}
+
+void syncthreads()
+{
+	Block *b = blk;
+	Fiber *f = curf;
+	const unsigned gen = b->bar_gen;
+	b->ticks++;
+	if (++b->bar_arrived == b->alive) {
+		b->bar_arrived = 0;
+		b->bar_gen++;
+		return;
+	}
+	f->bar_seen = gen;
+	f->wait = WAIT_BAR;
+	while (b->bar_gen == gen)
+		yield();
+	f->wait = RUN;
+}
+
+uint32_t warp_collect(uint32_t mask, uint64_t v, uint64_t out[32])
+{
+	Fiber *f = curf;
+	Warp &w = *f->ctx.warp;
+	const int lane = f->ctx.lane;
+	while (w.phase == 1) {			/* the previous collective is still being read by its participants */
+		f->wait = WAIT_DRAIN;
+		yield();
+	}
+	w.val[lane] = v;
+	w.arrived |= 1u << lane;
+	w.mask = mask;
+	blk->ticks++;
+	warp_try_release(w);
+	while (!(w.phase == 1 && ((w.part >> lane) & 1u))) {
+		f->wait = WAIT_WARP;
+		yield();
+	}
+	f->wait = RUN;
+	memcpy(out, w.val, sizeof(w.val));
+	const uint32_t part = w.part;
+	if (--w.left == 0) {
+		w.phase = 0;
+		w.arrived = 0;
+		blk->ticks++;
+	}
+	return part;
+}
+
+static inline bool runnable(const Block *b, const Fiber *f)
+{
+	if (f->done)
+		return false;
+	const Warp &w = *f->ctx.warp;
+	switch (f->wait) {
+	case WAIT_BAR: return b->bar_gen != f->bar_seen;
+	case WAIT_WARP: return w.phase == 1 && ((w.part >> f->ctx.lane) & 1u);
+	case WAIT_DRAIN: return w.phase == 0;
+	default: return true;
+	}
+}
+
+static void run_block(Block *b, dim3 grid, dim3 block, uint3 bid, size_t smem)
+{
+	const int n = (int) (block.x * block.y * block.z);
+	b->n = n;
+	b->alive = n;
+	b->bar_arrived = 0;
+	b->bar_gen = 0;
+	b->ticks = 0;
+	if (smem)
+		memset(b->smem, 0xCD, smem);		/* shared memory starts as garbage */
+	const int nwarps = (n + 31) / 32;
+	for (int w = 0; w < nwarps; w++) {
+		Warp &W = b->warps[w];
+		const int lanes = n - 32 * w >= 32 ? 32 : n - 32 * w;
+		W.alive = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1u);
+		W.arrived = W.part = W.mask = 0;
+		W.phase = W.left = 0;
+	}
+	for (int t = 0; t < n; t++) {
+		Fiber &f = b->fib[t];
+		f.done = false;
+		f.wait = RUN;
+		f.ctx.tid.x = t % block.x;
+		f.ctx.tid.y = (t / block.x) % block.y;
+		f.ctx.tid.z = t / (block.x * block.y);
+		f.ctx.bid = bid;
+		f.ctx.bdim = block;
+		f.ctx.gdim = grid;
+		f.ctx.lane = t & 31;
+		f.ctx.warp = &b->warps[t >> 5];
+		/* initial frame: six zeroed callee-saved registers, then the entry point as the return address */
+		uintptr_t top = (uintptr_t) (b->stacks + (size_t) (t + 1) * STACK_BYTES);
+		top &= ~(uintptr_t) 15;
+		void **sp = (void **) top;
+		*--sp = nullptr;			/* the return address fiber_entry never uses */
+		*--sp = (void *) fiber_entry;
+		for (int r = 0; r < 6; r++)
+			*--sp = nullptr;
+		f.sp = (void *) sp;
+	}
+	while (b->alive > 0) {
+		const unsigned long before = b->ticks;
+		for (int w = 0; w < nwarps; w++) {
+			/* keep a warp going until its lanes are finished or wait for the other warps */
+			for (;;) {
+				const unsigned long wbefore = b->ticks;
+				for (int t = 32 * w; t < n && t < 32 * w + 32; t++) {
+					Fiber *f = &b->fib[t];
+					if (!runnable(b, f))
+						continue;
+					curf = f;
+					cur = &f->ctx;
+					emu_switch(&b->sched_sp, f->sp);
+				}
+				if (b->ticks == wbefore)
+					break;
+			}
+		}
+		if (b->ticks == before) {
+			fprintf(stderr, "cuda_emu: deadlock in CTA (%u,%u,%u): %d threads alive, %d at the barrier\n", bid.x, bid.y,
+				bid.z, b->alive, b->bar_arrived);
+			abort();
+		}
+	}
+	cur = nullptr;
+	curf = nullptr;
+}
+
+void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
+{
+	const long total = (long) grid.x * grid.y * grid.z;
+	if (total <= 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > (unsigned) MAX_THREADS ||
+	    smem > DYN_SMEM_BYTES) {
+		fprintf(stderr, "cuda_emu: bad launch configuration (%u,%u,%u) x (%u,%u,%u), %zu bytes\n", grid.x, grid.y, grid.z,
+			block.x, block.y, block.z, smem);
+		abort();
+	}
+	/* CTAs are dealt to a few OS threads; every worker slot keeps its fiber stacks between launches */
+	static std::vector<Block *> pool;
+	static std::mutex pool_mutex;
+	std::lock_guard<std::mutex> guard(pool_mutex);		/* one launch at a time */
+	int workers = (int) std::thread::hardware_concurrency();
+	const char *e = getenv("STS_EMU_THREADS");
+	if (e && atoi(e) > 0)
+		workers = atoi(e);
+	if (workers > 16) workers = 16;
+	if (workers < 1) workers = 1;
+	if ((long) workers > total) workers = (int) total;
+	while ((int) pool.size() < workers)
+		pool.push_back(new_block());
+	std::atomic<long> next(0);
+	auto work = [&](int slot) {
+		Block *b = pool[slot];
+		blk = b;
+		b->body = &body;
+		for (long i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
+			uint3 bid;
+			bid.x = (unsigned) (i % grid.x);
+			bid.y = (unsigned) ((i / grid.x) % grid.y);
+			bid.z = (unsigned) (i / ((long) grid.x * grid.y));
+			run_block(b, grid, block, bid, smem);
+		}
+		blk = nullptr;
+	};
+	if (workers == 1) {
+		work(0);
+	} else {
+		std::vector<std::thread> th;
+		for (int w = 1; w < workers; w++)
+			th.emplace_back(work, w);
+		work(0);
+		for (auto &t : th)
+			t.join();
+	}
+}
+
+}	/* namespace emu */
+
+/* ---- runtime ------------------------------------------------------------------------------------ */
+struct emu_stream { int id; };
+struct emu_event { double t_ms; };
+
+static double now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d)
+{
+	if (d != 0)
+		return cudaErrorInvalidValue;
+	memset(p, 0, sizeof(*p));
+	snprintf(p->name, sizeof(p->name), "cuda_emu (CPU, tests only)");
+	p->major = 10;
+	p->minor = 0;
+	const char *e = getenv("STS_EMU_SMS");
+	p->multiProcessorCount = e && atoi(e) > 0 ? atoi(e) : 4;
+	p->totalGlobalMem = (size_t) 8 << 30;
+	p->sharedMemPerBlockOptin = 227 * 1024;
+	return cudaSuccess;
+}
+cudaError_t cudaDeviceGetPCIBusId(char *, int, int) { return cudaErrorNotSupported; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "cuda_emu error"); }
+cudaError_t cudaMalloc(void **p, size_t bytes)
+{
+	*p = nullptr;
+	if (posix_memalign(p, 256, bytes ? bytes : 1) != 0)
+		return cudaErrorMemoryAllocation;
+	memset(*p, 0xA5, bytes);			/* device memory starts as garbage */
+	return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void **p, size_t bytes)
+{
+	*p = nullptr;
+	return posix_memalign(p, 256, bytes ? bytes : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+			      cudaStream_t)
+{
+	for (size_t r = 0; r < height; r++)
+		memmove((char *) dst + r * dpitch, (const char *) src + r * spitch, width);
+	return cudaSuccess;
+}
+cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new emu_stream(); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event(); (*e)->t_ms = 0; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
