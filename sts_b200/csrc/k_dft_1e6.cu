@@ -209,8 +209,12 @@ dft_rows_1e6(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *_
 			}
 		}
 	}
-	cnt = (unsigned int) warp_sum((int) cnt);
-	if ((threadIdx.x & 31) == 0 && cnt)
+	/*
+	 * 200 threads = six warps and a quarter: the last warp has 8 lanes, and a full-mask shuffle reduction would
+	 * read lanes that do not exist (undefined values in CUDA - found by the CPU emulation of tests/emu, which
+	 * poisons them).  Every thread adds its own count instead: at most 200 shared-memory atomics per 2000 points.
+	 */
+	if (cnt)
 		atomicAdd(&cnt_s, cnt);
 	__syncthreads();
 	if (threadIdx.x == 0 && cnt_s)

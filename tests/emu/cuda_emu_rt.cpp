@@ -163,8 +163,9 @@ uint32_t warp_collect(uint32_t mask, uint64_t v, uint64_t out[32])
 		yield();
 	}
 	f->wait = RUN;
-	memcpy(out, w.val, sizeof(w.val));
 	const uint32_t part = w.part;
+	for (int l = 0; l < 32; l++)		/* reading a lane that does not take part is undefined in CUDA: poison it */
+		out[l] = ((part >> l) & 1u) ? w.val[l] : 0xDEADBEEFCAFEF00Dull;
 	if (--w.left == 0) {
 		w.phase = 0;
 		w.arrived = 0;

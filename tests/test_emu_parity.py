@@ -1,0 +1,67 @@
+"""CPU: the parity tests of tests/test_gpu_parity.py re-run with the engine's UNMODIFIED CUDA sources compiled for
+the functional emulator of tests/emu (fibers for the threads of a CTA, real warp collectives and barriers, a
+synchronous runtime).  Same test bodies, same bars (integers bit-exact, p-values within 1e-9 of the reference's
+golden values and of the oracle); only the `sts` fixture differs.
+
+What this does and does not show: the kernels' LOGIC - index arithmetic, bit extraction, the warp-collective and
+shared-memory algorithms, record layout, every host-side decision of engine.cu - is checked where no GPU exists,
+on every round's CPU run.  It is not a parity claim for the product (that is `-m gpu` on a B200: nvcc's code
+generation, libdevice, real concurrency and memory ordering are not emulated), nothing is timed on it, and the
+product never loads this library (tests/test_abi.py::test_product_never_imports_the_oracle, and
+sts_b200/binding.py refuses to run without its CUDA library).
+
+The slowest cases (tens of seconds each on the emulator) only run with STS_EMU_FULL=1."""
+import os
+
+import pytest
+
+import test_gpu_parity as G
+from emu_util import emu_binding
+
+FULL = os.environ.get("STS_EMU_FULL", "") not in ("", "0")
+slow = pytest.mark.skipif(not FULL, reason="slow on the emulator: set STS_EMU_FULL=1")
+
+
+@pytest.fixture(scope="module")
+def sts():
+    return emu_binding()
+
+
+def _pick(fn, keep):
+    """the parametrized test `fn` restricted to the parameter sets `keep` accepts (all of them with STS_EMU_FULL=1)"""
+    marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+    assert len(marks) == 1
+    names, values = marks[0].args[0], marks[0].args[1]
+    chosen = [v for v in values if FULL or keep(v)]
+
+    def test(sts, oracle, request):
+        kw = {k: request.getfixturevalue(k) for k in [x.strip() for x in names.split(",")]}
+        return fn(sts, oracle, **kw)
+    return pytest.mark.parametrize(names, chosen)(_rebind(fn, names))
+
+
+def _rebind(fn, names):
+    import functools
+    import types
+    g = types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+    g = functools.update_wrapper(g, fn)
+    g.pytestmark = [m for m in getattr(fn, "pytestmark", []) if m.name != "parametrize"]
+    del g.__wrapped__
+    return g
+
+
+# the golden vectors of the unmodified reference binary and the oracle, all 15 tests
+test_engine_matches_reference_golden_and_oracle = _pick(G.test_engine_matches_reference_golden_and_oracle,
+                                                        lambda case: case != "patterns_6")
+test_engine_config4_parameters = slow(_rebind(G.test_engine_config4_parameters, ""))
+test_device_lcg_is_the_reference_generator = _rebind(G.test_device_lcg_is_the_reference_generator, "")
+test_cyclic_pattern_histogram = _pick(G.test_cyclic_pattern_histogram, lambda bits: bits in (3, 16, 18))
+test_pipelined_batches_complete_in_order = _rebind(G.test_pipelined_batches_complete_in_order, "")
+test_assessment_tallies_match_reference_report = _rebind(G.test_assessment_tallies_match_reference_report, "")
+test_single_test_parameter_sweep = _pick(G.test_single_test_parameter_sweep, lambda v: True)
+test_partial_test_masks = _rebind(G.test_partial_test_masks, "")
+test_error_behaviour = _rebind(G.test_error_behaviour, "")
+test_small_streams_against_oracle = _pick(G.test_small_streams_against_oracle, lambda n: True)
+test_ascii_input_is_packed_like_the_reference_reads_it = _pick(G.test_ascii_input_is_packed_like_the_reference_reads_it,
+                                                               lambda line: True)
+test_ascii_input_short_text_and_bad_characters = _rebind(G.test_ascii_input_short_text_and_bad_characters, "")
