@@ -227,13 +227,50 @@ static void run_block(Block *b, dim3 grid, dim3 block, uint3 bid, size_t smem)
 			*--sp = nullptr;
 		f.sp = (void *) sp;
 	}
+	/*
+	 * STS_EMU_SCHED picks the order in which runnable fibers are resumed: "forward" (default: warp 0 first, lane 0
+	 * first), "reverse", or "random[:seed]" (a new permutation of warps and lanes on every pass).  Results must not
+	 * depend on it: a kernel that lacks a __syncthreads / __syncwarp between a write and a read of shared memory
+	 * gives different answers under different orders - a cheap race check.
+	 */
+	static const int sched = []() {
+		const char *e = getenv("STS_EMU_SCHED");
+		return e == nullptr ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r' && e[1] == 'a') ? 2 : 0;
+	}();
+	static const unsigned seed0 = []() {
+		const char *e = getenv("STS_EMU_SCHED");
+		const char *c = e ? strchr(e, ':') : nullptr;
+		return c ? (unsigned) atoi(c + 1) : 12345u;
+	}();
+	uint64_t rng = 0x9E3779B97F4A7C15ull * (seed0 + 1) + bid.x * 1000003ull + bid.y * 10007ull + bid.z;
+	int worder[MAX_THREADS / 32], lorder[32];
 	while (b->alive > 0) {
 		const unsigned long before = b->ticks;
-		for (int w = 0; w < nwarps; w++) {
+		for (int i = 0; i < nwarps; i++)
+			worder[i] = sched == 1 ? nwarps - 1 - i : i;
+		for (int i = 0; i < 32; i++)
+			lorder[i] = sched == 1 ? 31 - i : i;
+		if (sched == 2) {
+			for (int i = nwarps - 1; i > 0; i--) {
+				rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+				const int j = (int) ((rng >> 33) % (unsigned) (i + 1));
+				const int tmp = worder[i]; worder[i] = worder[j]; worder[j] = tmp;
+			}
+			for (int i = 31; i > 0; i--) {
+				rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+				const int j = (int) ((rng >> 33) % (unsigned) (i + 1));
+				const int tmp = lorder[i]; lorder[i] = lorder[j]; lorder[j] = tmp;
+			}
+		}
+		for (int wi = 0; wi < nwarps; wi++) {
+			const int w = worder[wi];
 			/* keep a warp going until its lanes are finished or wait for the other warps */
 			for (;;) {
 				const unsigned long wbefore = b->ticks;
-				for (int t = 32 * w; t < n && t < 32 * w + 32; t++) {
+				for (int li = 0; li < 32; li++) {
+					const int t = 32 * w + lorder[li];
+					if (t >= n)
+						continue;
 					Fiber *f = &b->fib[t];
 					if (!runnable(b, f))
 						continue;
