@@ -17,12 +17,16 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "sts_b200", "csrc")
-BUILD = os.path.join(HERE, "_build")
+# STS_EMU_ASAN=1: a second build with AddressSanitizer (tests/emu/_build_asan), for hunting out-of-bounds accesses of
+# device / pinned buffers by kernels and host code; run python with LD_PRELOAD=$(g++ -print-file-name=libasan.so)
+# ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
+ASAN = os.environ.get("STS_EMU_ASAN", "") not in ("", "0")
+BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(BUILD, "libstsgpu_emu.so")
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-Wno-unknown-pragmas",
          "-include", os.path.join(HERE, "cuda_emu.h"), "-I", os.path.join(HERE, "stub"), "-I", CSRC,
-         "-I", os.path.join(ROOT, "include")]
+         "-I", os.path.join(ROOT, "include")] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else [])
 
 
 def _balanced(s, i, open_ch, close_ch):
@@ -134,7 +138,7 @@ def build(force=False, verbose=False):
             failed |= rc != 0
     if failed:
         raise SystemExit("cuda_emu build failed")
-    subprocess.check_call([CXX, "-shared", "-pthread", "-o", LIB] + [j[1] for j in jobs] + ["-ldl", "-lm", "-lpthread"])
+    subprocess.check_call([CXX, "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + ["-o", LIB] + [j[1] for j in jobs] + ["-ldl", "-lm", "-lpthread"])
     return LIB
 
 

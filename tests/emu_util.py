@@ -52,6 +52,7 @@ def emu_host_driver():
     srcs = [os.path.join(host, "stsb200.c"), os.path.join(host, "sts_host.c")]
     deps = srcs + [os.path.join(host, "sts_host.h"), lib]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-I", os.path.join(ROOT, "include")] + srcs +
+        asan = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("STS_EMU_ASAN", "") not in ("", "0") else []
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-I", os.path.join(ROOT, "include")] + asan + srcs +
                               ["-L", build, "-lstsgpu_emu", "-Wl,-rpath," + build, "-lpthread", "-lm", "-o", exe])
     return exe
