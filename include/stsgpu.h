@@ -157,10 +157,11 @@ int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out);
  */
 int stsgpu_query_layout(const stsgpu_params *p, stsgpu_layout *out);
 /*
- * 1 if the engine's FFT can take streams of n bits: n/2 must split into two 5-smooth factors small
- * enough for its register-resident passes (every power of two up to 2^25, 10^6, 10^7 ...).  The reference's libfftw3 plan
- * (discreteFourierTransform.c:194) takes any n; for other n stsgpu_create refuses the DFT test
- * with STSGPU_E_UNSUPPORTED unless bit 7 of test_mask is clear - never a CPU fallback.
+ * 1 if the engine's FFT can take streams of n bits.  Like the reference's libfftw3 plan
+ * (discreteFourierTransform.c:194) it takes any even n: the four-step kernels when n/2 splits into two 5-smooth
+ * factors of at most 4096 (every power of two up to 2^25, 10^6, 10^7 ...), a Bluestein FFT otherwise - up to
+ * n = 2^25.  Only longer streams with a non-5-smooth half are refused: stsgpu_create then fails with
+ * STSGPU_E_UNSUPPORTED unless bit 7 of test_mask is clear - never a CPU fallback.
  */
 int stsgpu_dft_supported(int64_t n);
 

@@ -121,7 +121,7 @@ def load_library():
 
 
 def dft_supported(n):
-    """can the engine's FFT take streams of n bits (n/2 = two 5-smooth factors <= 3200)"""
+    """can the engine's FFT take streams of n bits (any even n up to 2^25; beyond that n/2 = two 5-smooth factors <= 4096)"""
     return bool(load_library().stsgpu_dft_supported(n))
 
 

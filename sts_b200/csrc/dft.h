@@ -11,7 +11,7 @@ struct DftPlan {
 	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
 	int threads;		/* CTA size of the generic kernels (256 or 512) */
-	int fast;		/* 1: n = 2^20, the kernels of k_dft_fast.cu; 2: n = 10^6, k_dft_1e6.cu; 0: generic */
+	int fast;		/* 1: n = 2^20, the kernels of k_dft_fast.cu; 2: n = 10^6, k_dft_1e6.cu; 3: any n, k_dft_any.cu; 0: generic */
 	/* per-pass twiddles, pass p at offset off[p]: entry (r - 1) Ns + k = exp(-2 pi i k r / (Ns R)), so that
 	 * consecutive butterflies (consecutive k) read consecutive table entries */
 	const double2 *w1;
@@ -37,8 +37,19 @@ struct DftPlan {
 	const double2 *m_e2;	/* [1000]: exp(-2 pi i 50 j2 / N) */
 	const double2 *m_p1;	/* [500]:  exp(-2 pi i k1 / n) */
 	const double2 *m_p2;	/* [1000]: exp(-2 pi i 500 k2 / n) */
+	/* Bluestein path for n/2 that is not 5-smooth (k_dft_any.cu, fast == 3), NULL / 0 otherwise */
+	long long bs_M;		/* convolution length, the power of two >= 2 N - 1 */
+	int bs_logM;
+	const double2 *bs_chirp;	/* [N]:       exp(-i pi j^2 / N) */
+	const double2 *bs_bhat;	/* [M]:       FFT_M of the wrapped conjugate chirp, divided by M */
+	const double2 *bs_tw;	/* [M/2]:     exp(-2 pi i t / M) */
+	const double2 *bs_wq;	/* [N/2 + 1]: exp(-2 pi i q / n) */
 	double T;		/* sqrt(log(20) * n), discreteFourierTransform.c:142 */
 };
 
-/* host side (k_dft.cu): split N = n/2 into N1 x N2 and radix lists; false if n is not supported */
+/* host side (k_dft.cu): split N = n/2 into N1 x N2 and radix lists; false if n/2 is not 5-smooth (or too long) */
 bool dft_make_plan(long long n, DftPlan *D);
+/* host side (k_dft_any.cu): the Bluestein plan for every other even n up to 2^25; tables; launches per chunk */
+bool dft_any_plan(long long n, DftPlan *D);
+cudaError_t dft_any_setup(long long n, DftPlan *D, double2 *tabs[4], int num_sms);
+int dft_any_launches_per_chunk(const DftPlan &D);

@@ -394,10 +394,12 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	int logn = 0;
 	while ((1LL << logn) < n) logn++;
 	if (en & (1u << STSGPU_TEST_DFT)) {
-		if (!dft_make_plan(n, &ctx->dft))
+		ctx->dft.fast = 0;
+		ctx->dft.bs_M = 0;
+		if (!dft_make_plan(n, &ctx->dft) && !dft_any_plan(n, &ctx->dft))
 			return fail_create(ctx, STSGPU_E_UNSUPPORTED,
-					   "DFT test: n/2 must split into two 5-smooth factors of at most ~4000 (powers of two up to 2^23, "
-					   "10^6, 10^7 ...); clear bit 7 of test_mask for other stream lengths");
+					   "DFT test: streams longer than 2^25 bits need n/2 = two 5-smooth factors of at most 4096; "
+					   "clear bit 7 of test_mask for this stream length");
 	}
 
 	/* ---- tail constants (host libm, reference expressions) ---- */
@@ -550,10 +552,22 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	}
 	if (en & (1u << STSGPU_TEST_DFT)) {
 		DftPlan &D = ctx->dft;				/* N1, N2, radix lists: dft_make_plan above */
-		const int N1 = D.N1, N2 = D.N2;
-		const int64_t N = (int64_t) N1 * N2;
-		D.fast = (n == (1LL << 20)) ? 1 : (n == 1000000 ? 2 : 0);
+		const bool any = D.fast == 3;			/* Bluestein (k_dft_any.cu): n/2 is not 5-smooth */
+		const int N1 = any ? 1 : D.N1, N2 = any ? 1 : D.N2;
+		const int64_t N = any ? D.bs_M : (int64_t) N1 * N2;	/* elements of one stream in a work buffer */
+		if (!any)
+			D.fast = (n == (1LL << 20)) ? 1 : (n == 1000000 ? 2 : 0);
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
+		D.w1 = D.w2 = D.tl = D.th = D.p1 = D.p2 = nullptr;
+		D.bs_chirp = D.bs_bhat = D.bs_tw = D.bs_wq = nullptr;
+		if (any) {
+			double2 *tabs[4];
+			const cudaError_t e_any = dft_any_setup(n, &D, tabs, ctx->num_sms);
+			for (int i = 0; i < 4; i++)
+				ctx->dft_tabs[5 + i] = tabs[i];
+			CKC(e_any, "DFT (Bluestein) tables");
+		}
+		if (!any) {
 		std::vector<double2> w1(N1), w2(N2), tl(1024), th((size_t) (N / 1024 + 1)), p1(N1), p2(N2);
 		{	/* per-pass twiddle tables (dft.h): entry (r - 1) Ns + k of pass p = exp(-2 pi i k r / (Ns R)) */
 			for (int which = 0; which < 2; which++) {
@@ -629,6 +643,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			D.m_twA = d + o[0]; D.m_twB = d + o[1]; D.m_twC = d + o[2]; D.m_twD = d + o[3];
 			D.m_e1 = d + o[4]; D.m_e2 = d + o[5]; D.m_p1 = d + o[6]; D.m_p2 = d + o[7];
 		}
+		}	/* !any */
 		int64_t chunk = 128;
 		const char *envc = getenv("STSGPU_DFT_CHUNK");
 		if (envc && atoi(envc) > 0) chunk = atoi(envc);
@@ -690,7 +705,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 extern "C" int stsgpu_dft_supported(int64_t n)
 {
 	DftPlan D;
-	return dft_make_plan(n, &D) ? 1 : 0;
+	return (dft_make_plan(n, &D) || dft_any_plan(n, &D)) ? 1 : 0;
 }
 
 extern "C" int stsgpu_get_layout(const stsgpu_ctx *ctx, stsgpu_layout *out)
@@ -766,7 +781,8 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		case G_LC: e = launch_lc(P, L, ctx->d_class_lut); launched = 1; break;
 		case G_DFT:
 			e = launch_dft(P, L, ctx->dft, S.d_dft_work, ctx->dft_chunk);
-			launched = (P.enabled & (1u << STSGPU_TEST_DFT)) ? 2 * ((nstreams + ctx->dft_chunk - 1) / ctx->dft_chunk) : 0;
+			launched = (P.enabled & (1u << STSGPU_TEST_DFT))
+				? (ctx->dft.fast == 3 ? dft_any_launches_per_chunk(ctx->dft) : 2) * ((nstreams + ctx->dft_chunk - 1) / ctx->dft_chunk) : 0;
 			break;
 		}
 		if (e != cudaSuccess) {

@@ -62,9 +62,12 @@ def test_product_never_imports_the_oracle():
 
 
 def test_dft_supported_lengths():
-    """host-side FFT planning (no CUDA call): n/2 must split into two 5-smooth factors that fit the register-resident passes"""
+    """host-side FFT planning (no CUDA call): n/2 = two 5-smooth factors takes the four-step kernels, every other even n
+    up to 2^25 the Bluestein path (k_dft_any.cu); beyond that only the 5-smooth splits, and a longer stream is refused"""
     import sts_b200 as sts
     for n in (1 << 10, 1 << 16, 1 << 20, 1 << 23, 1 << 25, 10 ** 6, 10 ** 7, 400000, 3 * (1 << 18)):
         assert sts.dft_supported(n), n
-    for n in (1000008, 2 * 1000003, 14 * (1 << 16), 1 << 27):
+    for n in (1000008, 2 * 1000003, 14 * (1 << 16), 8072, (1 << 25) - 8):      # not 5-smooth: Bluestein, M <= 2^25
+        assert sts.dft_supported(n), n
+    for n in (1 << 27, (1 << 25) + 8, 7 * (1 << 23)):
         assert not sts.dft_supported(n), n

@@ -33,7 +33,7 @@ def engine_for(sts, g, streams, mask=None):
     n = prm["n"]
     m = sts.ALL_TESTS if mask is None else mask
     if not sts.dft_supported(n):
-        m &= ~(1 << 7)               # n/2 not 5-smooth: the engine refuses the DFT loudly
+        m &= ~(1 << 7)               # beyond the engine's FFT lengths: it refuses the DFT loudly
     return sts.Engine(max_streams=streams, test_mask=m, **prm), m
 
 
@@ -276,6 +276,10 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     (7, dict(n=1 << 22)),                                # DFT: generic path above the fast kernel's length
     (7, dict(n=1 << 25)),                                # DFT: 4096 x 4096, the largest split
     (7, dict(n=3 * 5 * (1 << 15))),                      # DFT: radices 3 and 5 together
+    (7, dict(n=1000008)),                                # DFT: n/2 = 2^2 3^2 17 19 43 - Bluestein path, M = 2^20
+    (7, dict(n=7 * (1 << 17))),                          # DFT: Bluestein, M = 2^20 reached exactly from 2N - 1 < M
+    (7, dict(n=8072)),                                   # DFT: Bluestein, odd log2 M (one radix-2 pass), N = 4 x 1009
+    (7, dict(n=8 * 1031)),                               # DFT: Bluestein, N = 4 x 1031, M = 2^14 (radix 4 only)
 ])
 def test_single_test_parameter_sweep(sts, oracle, test, prm):
     """kernel variants the default parameters never reach, one test at a time, bit-exact / 1e-9 against the oracle"""
@@ -314,7 +318,7 @@ def test_error_behaviour(sts):
     with pytest.raises(sts.EngineError):
         sts.Engine(max_streams=1, n=1001)                    # n % 8 != 0  (parse_args.c:939)
     with pytest.raises(sts.EngineError):
-        sts.Engine(max_streams=1, n=1000008)                 # DFT with n/2 not 5-smooth: unsupported, said loudly
+        sts.Engine(max_streams=1, n=(1 << 25) + 8)           # DFT beyond 2^25 bits with n/2 not 5-smooth: refused loudly
     with sts.Engine(max_streams=2) as eng:
         with pytest.raises(sts.EngineError):
             eng.wait()                                       # wait without submit
