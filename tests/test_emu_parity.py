@@ -95,3 +95,7 @@ def test_results_do_not_depend_on_the_thread_schedule(sts):
         assert r.returncode == 0, r.stderr[-2000:]
         digests[sched] = r.stdout.strip()
     assert len(set(digests.values())) == 1, digests
+
+
+test_repeated_batches_on_one_engine_give_identical_records = _pick(G.test_repeated_batches_on_one_engine_give_identical_records,
+                                                                   lambda prm: prm.get("n") in (10 ** 6, 1000008))
