@@ -99,3 +99,4 @@ def test_results_do_not_depend_on_the_thread_schedule(sts):
 
 test_repeated_batches_on_one_engine_give_identical_records = _pick(G.test_repeated_batches_on_one_engine_give_identical_records,
                                                                    lambda prm: prm.get("n") in (10 ** 6, 1000008))
+test_engine_limits_against_oracle = _pick(G.test_engine_limits_against_oracle, lambda test, prm: test == 14)

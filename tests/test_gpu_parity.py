@@ -473,3 +473,21 @@ def test_repeated_batches_on_one_engine_give_identical_records(sts, oracle, prm)
     for x, y, z in zip(first, again, alone):
         assert (x == y).all() and (x == z).all()
     assert mask != 0
+
+
+@pytest.mark.parametrize("test,prm", [
+    (14, dict(n=1 << 24, serial_m=21)),                  # Serial at the engine's largest block length (64 histogram slices)
+    (11, dict(n=1 << 26, apen_m=20)),                    # ApEn at the engine's largest block length (H = 21), 8 MiB streams
+    (10, dict(n=1010 * (1 << 15) * 15)),                 # Universal L = 15, the largest table the engine takes (n = 496 Mbit)
+])
+def test_engine_limits_against_oracle(sts, oracle, test, prm):
+    """the largest parameters the engine accepts: one stream each, against the oracle"""
+    base = dict(n=1 << 20, block_frequency_M=16384, non_overlapping_m=9, overlapping_m=9, apen_m=10, serial_m=16,
+                linear_complexity_M=500)
+    base.update(prm)
+    mask = 1 << test
+    raw = oracle.lcg_bytes(3, 1, base["n"])
+    with sts.Engine(max_streams=1, test_mask=mask, **base) as eng:
+        assert eng.layout.enabled_mask == mask == oracle.layout(oracle.make_params(test_mask=mask, **base)).enabled_mask
+        pv, st, w = eng.run(raw, 1)
+        compare_with_oracle(sts, oracle, eng, mask, base, raw, 1, pv, st, w)
