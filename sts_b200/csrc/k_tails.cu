@@ -373,13 +373,13 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
 				const long long i = base + 4 * lane + j;
-				double term = 0.0;
+				double mterm = 0.0;		/* -C log(C / n) >= 0; an empty bin adds +0.0, not -0.0 */
 				if (i < bins) {
 					const uint32_t C = hr[i];
 					if (C)
-						term = (double) C * log(C / (double) n);
+						mterm = -((double) C * log(C / (double) n));
 				}
-				tm[j] = -term;
+				tm[j] = mterm;
 			}
 			const double4 t4 = make_double4(tm[0], tm[1], tm[2], tm[3]);
 			if (!warp_rne_sum128(mag, t4, lane)) {

@@ -28,7 +28,9 @@ __device__ __forceinline__ RneMap rne_of_term(double x, int k)
 	RneMap f;
 	f.a0 = 0;
 	f.dl = 0;
-	const unsigned long long xb = (unsigned long long) __double_as_longlong(x);
+	/* the sign bit is dropped: the terms are >= 0 by contract, and a -0.0 (the negated empty bin of the ApEn sum) must
+	 * count as zero - taken as a number it has "exponent" 1025 and a negative shift below (found by tests/emu) */
+	const unsigned long long xb = (unsigned long long) __double_as_longlong(x) & 0x7FFFFFFFFFFFFFFFull;
 	if (xb != 0) {
 		const int e = (int) (xb >> 52) - 1023;
 		const unsigned long long M = (xb & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool warp_rne_sum128(double &sum, const double4 &t, i
 	const unsigned long long sb = (unsigned long long) __double_as_longlong(sum);
 	const int k = (int) (sb >> 52) - 1023;
 	const double tm = fmax(fmax(t.x, t.y), fmax(t.z, t.w));
-	const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int) __double2hiint(tm));
+	const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int) __double2hiint(tm) & 0x7FFFFFFFu);
 	const int emax = (int) (hi >> 20) - 1023;
 	if (k < emax + 2 || k < -1000)
 		return false;
@@ -115,7 +117,7 @@ __device__ __forceinline__ bool warp_rne_sum_rows(double &sum, const double *tb,
 	for (int j = 0; j < nrows; j++) {
 		const int i = lane * nrows + j;
 		const double x = tb[(i >> 5) * 33 + (i & 31)];
-		const unsigned int hi = (unsigned int) __double2hiint(x);
+		const unsigned int hi = (unsigned int) __double2hiint(x) & 0x7FFFFFFFu;
 		himax = max(himax, hi);
 		/* a term too large for this binade is caught below; keep the shift in range meanwhile */
 		f = rne_compose(f, rne_of_term(x, max(k, (int) (hi >> 20) - 1023 + 2)));

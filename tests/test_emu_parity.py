@@ -100,3 +100,23 @@ def test_results_do_not_depend_on_the_thread_schedule(sts):
 test_repeated_batches_on_one_engine_give_identical_records = _pick(G.test_repeated_batches_on_one_engine_give_identical_records,
                                                                    lambda prm: prm.get("n") in (10 ** 6, 1000008))
 test_engine_limits_against_oracle = _pick(G.test_engine_limits_against_oracle, lambda test, prm: test == 14)
+
+
+def test_apen_sum_with_empty_bins_is_the_sequential_sum(sts, oracle):
+    """ApEn's phi = (1/n) sum C log(C/n) in index order (approximateEntropy.c:396-407) on a 7/8-biased stream, whose
+    histograms have hundreds of empty bins: the exact parallel summation (rne_sum.cuh) must give the oracle's
+    sequential double bit for bit (same libm here).  It used to add one unit in the last place per empty bin that went
+    through its fast path - the negated empty bin is -0.0, which was decoded as a number - inside the 1e-13 the GPU
+    test allows for libdevice's log, so only the emulator's exact comparison could see it."""
+    import numpy as np
+    from golden_util import pattern_streams
+    n = 1 << 20
+    raw = pattern_streams(n, 6).reshape(6, -1)[5].copy()
+    for m in (10, 7):
+        with sts.Engine(max_streams=1, test_mask=1 << 11, apen_m=m) as eng:
+            pv, st, w = eng.run(raw, 1)
+            got = st[0, eng.layout.st_off[11]:eng.layout.st_off[11] + 2].copy()
+        opv, ost, ow, olay = oracle.run(oracle.make_params(test_mask=1 << 11, apen_m=m), raw, 1)
+        want = ost[0, olay.st_off[11]:olay.st_off[11] + 2]
+        assert (got == want).all(), (got.view(np.float64), want.copy().view(np.float64))
+        assert (pv == opv).all()
