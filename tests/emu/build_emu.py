@@ -21,12 +21,17 @@ CSRC = os.path.join(ROOT, "sts_b200", "csrc")
 # device / pinned buffers by kernels and host code; run python with LD_PRELOAD=$(g++ -print-file-name=libasan.so)
 # ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
 ASAN = os.environ.get("STS_EMU_ASAN", "") not in ("", "0")
-BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
+# STS_EMU_UBSAN=1: the same with UndefinedBehaviorSanitizer (tests/emu/_build_ubsan): shift counts out of range,
+# signed overflow, misaligned or out-of-bounds accesses - x86 and the GPU resolve these differently, so each report
+# is a place where the emulator and the hardware may disagree
+UBSAN = os.environ.get("STS_EMU_UBSAN", "") not in ("", "0")
+BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build_ubsan" if UBSAN else "_build")
 LIB = os.path.join(BUILD, "libstsgpu_emu.so")
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-Wno-unknown-pragmas",
          "-include", os.path.join(HERE, "cuda_emu.h"), "-I", os.path.join(HERE, "stub"), "-I", CSRC,
-         "-I", os.path.join(ROOT, "include")] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else [])
+         "-I", os.path.join(ROOT, "include")] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + \
+    (["-fsanitize=undefined", "-fno-sanitize=vptr", "-fno-omit-frame-pointer"] if UBSAN else [])
 
 
 def _balanced(s, i, open_ch, close_ch):
@@ -138,7 +143,7 @@ def build(force=False, verbose=False):
             failed |= rc != 0
     if failed:
         raise SystemExit("cuda_emu build failed")
-    subprocess.check_call([CXX, "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + ["-o", LIB] + [j[1] for j in jobs] + ["-ldl", "-lm", "-lpthread"])
+    subprocess.check_call([CXX, "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=undefined"] if UBSAN else []) + ["-o", LIB] + [j[1] for j in jobs] + ["-ldl", "-lm", "-lpthread"])
     return LIB
 
 
