@@ -87,7 +87,13 @@ template <class T> static inline T from_bits(uint64_t b)
 #define gridDim (emu::cur->gdim)
 #define warpSize 32
 
-#define EMU_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (size_t) (smem), [=]() { kernel(__VA_ARGS__); })
+/* dynamic shared memory above 48 KiB needs cudaFuncSetAttribute(MaxDynamicSharedMemorySize) first, as on the device */
+void emu_set_max_dyn_smem(const void *kernel, int bytes);
+bool emu_check_dyn_smem(const void *kernel, size_t bytes, const char *name);	/* false: cudaGetLastError() reports it */
+#define EMU_LAUNCH(kernel, grid, block, smem, stream, ...)                                                        \
+	(emu_check_dyn_smem(reinterpret_cast<const void *>(&kernel), (size_t) (smem), #kernel)                   \
+		 ? emu::launch((grid), (block), (size_t) (smem), [=]() { kernel(__VA_ARGS__); })                  \
+		 : (void) 0)
 
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu)
@@ -339,6 +345,14 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
-template <class T> static inline cudaError_t cudaFuncSetAttribute(T *, int, int) { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaFuncSetAttribute(T *f, int attr, int v)
+{
+	if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+		if (v > 227 * 1024)
+			return cudaErrorInvalidValue;
+		emu_set_max_dyn_smem(reinterpret_cast<const void *>(f), v);
+	}
+	return cudaSuccess;
+}
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **) p, bytes); }
 template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMallocHost((void **) p, bytes); }

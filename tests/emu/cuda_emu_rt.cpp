@@ -296,7 +296,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &b
 {
 	const long total = (long) grid.x * grid.y * grid.z;
 	if (total <= 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > (unsigned) MAX_THREADS ||
-	    smem > DYN_SMEM_BYTES) {
+	    smem > DYN_SMEM_BYTES || grid.y > 65535u || grid.z > 65535u || grid.x > 2147483647u) {	/* the device's limits */
 		fprintf(stderr, "cuda_emu: bad launch configuration (%u,%u,%u) x (%u,%u,%u), %zu bytes\n", grid.x, grid.y, grid.z,
 			block.x, block.y, block.z, smem);
 		abort();
@@ -343,6 +343,28 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &b
 }	/* namespace emu */
 
 /* ---- runtime ------------------------------------------------------------------------------------ */
+#include <map>
+static std::map<const void *, int> g_max_dyn_smem;
+static std::mutex g_attr_mutex;
+void emu_set_max_dyn_smem(const void *kernel, int bytes)
+{
+	std::lock_guard<std::mutex> g(g_attr_mutex);
+	g_max_dyn_smem[kernel] = bytes;
+}
+static cudaError_t g_last_error = cudaSuccess;
+bool emu_check_dyn_smem(const void *kernel, size_t bytes, const char *name)
+{
+	std::lock_guard<std::mutex> g(g_attr_mutex);
+	const auto it = g_max_dyn_smem.find(kernel);
+	const size_t limit = it == g_max_dyn_smem.end() ? 48 * 1024 : (size_t) (it->second > 48 * 1024 ? it->second : 48 * 1024);
+	if (bytes > limit) {
+		fprintf(stderr, "cuda_emu: launch of %s asks for %zu bytes of dynamic shared memory, the limit set for it is %zu "
+			"(cudaErrorInvalidValue on the device)\n", name, bytes, limit);
+		g_last_error = cudaErrorInvalidValue;
+		return false;
+	}
+	return true;
+}
 struct emu_stream { int id; };
 struct emu_event { double t_ms; };
 
@@ -373,7 +395,13 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d)
 cudaError_t cudaDeviceGetPCIBusId(char *, int, int) { return cudaErrorNotSupported; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void)
+{
+	std::lock_guard<std::mutex> g(g_attr_mutex);
+	const cudaError_t e = g_last_error;
+	g_last_error = cudaSuccess;
+	return e;
+}
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "cuda_emu error"); }
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
