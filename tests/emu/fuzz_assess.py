@@ -50,3 +50,4 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
                 print("   ", k, d[:5].tolist(), np.asarray(a[k])[tuple(d[0])], np.asarray(o[k])[tuple(d[0])])
         bad += 1
 print("bad", bad)
+sys.exit(1 if bad else 0)
