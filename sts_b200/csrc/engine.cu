@@ -389,6 +389,10 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 					   "Serial/ApEn block lengths outside the engine's range (3 <= serial m <= 21, "
 					   "1 <= apen m <= 20, levels spread < 15 bits)");
 	}
+	if ((en & (1u << STSGPU_TEST_LINEARCOMPLEXITY)) && P.lc_M > 1022 && (P.lc_N + 3) / 4 > 65535)
+		/* the warp-per-block kernel puts four blocks in a CTA and the CTAs of a stream along grid.y (k_lc.cu) */
+		return fail_create(ctx, STSGPU_E_UNSUPPORTED,
+				   "LinearComplexity with M > 1022 on streams of more than 262140 blocks (n > 2.6e8 bits) is not supported");
 	if ((en & (1u << STSGPU_TEST_UNIVERSAL)) && L > 15)
 		return fail_create(ctx, STSGPU_E_UNSUPPORTED, "Universal test with L = 16 (n >= 1.06e9 bits) is not supported");
 	int logn = 0;
