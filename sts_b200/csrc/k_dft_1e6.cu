@@ -212,9 +212,14 @@ dft_rows_1e6(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *_
 	/*
 	 * 200 threads = six warps and a quarter: the last warp has 8 lanes, and a full-mask shuffle reduction would
 	 * read lanes that do not exist (undefined values in CUDA - found by the CPU emulation of tests/emu, which
-	 * poisons them).  Every thread adds its own count instead: at most 200 shared-memory atomics per 2000 points.
+	 * poisons them; the hardware happened to deliver zeros).  The reduction names exactly the lanes the warp has.
 	 */
-	if (cnt)
+	{
+		const unsigned int left = blockDim.x - (threadIdx.x & ~31u);		/* threads from this warp's lane 0 on */
+		const unsigned int lanes = left >= 32u ? 0xFFFFFFFFu : ((1u << left) - 1u);
+		cnt = __reduce_add_sync(lanes, cnt);
+	}
+	if ((threadIdx.x & 31) == 0 && cnt)
 		atomicAdd(&cnt_s, cnt);
 	__syncthreads();
 	if (threadIdx.x == 0 && cnt_s)
