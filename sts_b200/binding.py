@@ -64,6 +64,7 @@ def build_library(force=False):
 
 
 _lib = None
+_ALLOW_EMULATION = False	# only tests/emu_util.py sets this, on its private copy of this module
 
 
 def load_library():
@@ -73,6 +74,9 @@ def load_library():
     if not os.path.exists(_LIBNAME):
         raise EngineError("%s is missing: run `make -C sts_b200` (there is no CPU fallback)" % _LIBNAME)
     lib = C.CDLL(_LIBNAME)
+    if hasattr(lib, "stsgpu_is_emulation") and not _ALLOW_EMULATION:
+        raise EngineError("%s is the CPU emulation of tests/emu - test infrastructure, never a fallback: the product "
+                          "only runs on the CUDA build of sts_b200/libstsgpu.so" % _LIBNAME)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     lib.stsgpu_default_params.argtypes = [C.POINTER(Params)]
     lib.stsgpu_default_params.restype = None

@@ -38,6 +38,7 @@ def emu_binding():
             else:
                 os.environ["STSGPU_LIB"] = old
         assert mod.library_path() == lib
+        mod._ALLOW_EMULATION = True		# the product's own instance of the binding refuses this library
         mod.load_library()
         _mod = mod
     return _mod

@@ -71,3 +71,21 @@ def test_dft_supported_lengths():
         assert sts.dft_supported(n), n
     for n in (1 << 27, (1 << 25) + 8, 7 * (1 << 23)):
         assert not sts.dft_supported(n), n
+
+
+def test_product_binding_refuses_the_emulation_library():
+    """the CPU emulation of tests/emu is test infrastructure: pointing the product's binding at it (STSGPU_LIB) is an
+    error, not a way to run without a GPU"""
+    import subprocess
+    import sys
+    from emu_util import emu_library
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import sts_b200\n"
+            "try:\n"
+            "    sts_b200.load_library()\n"
+            "    print('LOADED')\n"
+            "except sts_b200.EngineError as e:\n"
+            "    print('REFUSED', e)\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, STSGPU_LIB=emu_library()), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert "REFUSED" in r.stdout and "never a fallback" in r.stdout, r.stdout
