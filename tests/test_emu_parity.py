@@ -121,3 +121,4 @@ def test_apen_sum_with_empty_bins_is_the_sequential_sum(sts, oracle):
         want = ost[0, olay.st_off[11]:olay.st_off[11] + 2]
         assert (got == want).all(), (got.view(np.float64), want.copy().view(np.float64))
         assert (pv == opv).all()
+test_dft_bluestein_path = _pick(G.test_dft_bluestein_path, lambda n: True)

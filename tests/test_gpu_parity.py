@@ -28,12 +28,22 @@ def sts():
     return sts_b200
 
 
+def half_is_5_smooth(n):
+    h = n // 2
+    for p in (2, 3, 5):
+        while h % p == 0:
+            h //= p
+    return h == 1
+
+
 def engine_for(sts, g, streams, mask=None):
     prm = golden_params(g)
     n = prm["n"]
     m = sts.ALL_TESTS if mask is None else mask
-    if not sts.dft_supported(n):
-        m &= ~(1 << 7)               # beyond the engine's FFT lengths: it refuses the DFT loudly
+    if not sts.dft_supported(n) or not half_is_5_smooth(n):
+        # beyond the engine's FFT lengths it refuses the DFT loudly; the Bluestein lengths have their own
+        # test at the end of this file (test_dft_bluestein_path), so that the four-step kernels are judged first
+        m &= ~(1 << 7)
     return sts.Engine(max_streams=streams, test_mask=m, **prm), m
 
 
@@ -276,10 +286,6 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     (7, dict(n=1 << 22)),                                # DFT: generic path above the fast kernel's length
     (7, dict(n=1 << 25)),                                # DFT: 4096 x 4096, the largest split
     (7, dict(n=3 * 5 * (1 << 15))),                      # DFT: radices 3 and 5 together
-    (7, dict(n=1000008)),                                # DFT: n/2 = 2^2 3^2 17 19 43 - Bluestein path, M = 2^20
-    (7, dict(n=7 * (1 << 17))),                          # DFT: Bluestein, M = 2^20 reached exactly from 2N - 1 < M
-    (7, dict(n=8072)),                                   # DFT: Bluestein, odd log2 M (one radix-2 pass), N = 4 x 1009
-    (7, dict(n=8 * 1031)),                               # DFT: Bluestein, N = 4 x 1031, M = 2^14 (radix 4 only)
 ])
 def test_single_test_parameter_sweep(sts, oracle, test, prm):
     """kernel variants the default parameters never reach, one test at a time, bit-exact / 1e-9 against the oracle"""
@@ -452,7 +458,7 @@ def test_contexts_are_independent_and_release_their_memory(sts, oracle):
 @pytest.mark.parametrize("prm", [
     dict(),                                                              # n = 2^20: the specialised FFT kernels
     dict(n=10 ** 6),                                                     # n = 10^6: 200-thread CTAs (partial last warp)
-    dict(n=1000008, linear_complexity_M=1100, serial_m=9, apen_m=7),     # ragged words, Bluestein FFT, warp-per-block LC
+    dict(n=1000008, linear_complexity_M=1100, serial_m=9, apen_m=7),     # ragged words, warp-per-block LC
     dict(n=1 << 17),                                                     # short streams: most tests disabled
 ])
 def test_repeated_batches_on_one_engine_give_identical_records(sts, oracle, prm):
@@ -463,6 +469,8 @@ def test_repeated_batches_on_one_engine_give_identical_records(sts, oracle, prm)
     not exist - that the single-batch tests could not see.)"""
     n = prm.get("n", 1 << 20)
     a, b = oracle.lcg_bytes(50, 3, n), oracle.lcg_bytes(60, 2, n)
+    if not half_is_5_smooth(n):
+        prm = dict(prm, test_mask=sts.ALL_TESTS & ~(1 << 7))     # the Bluestein FFT is judged by the last test of this file
     with sts.Engine(max_streams=3, pipeline_depth=2, **prm) as eng:
         first = eng.run(a, 3, 0)
         eng.run(b, 2, 3)
@@ -491,3 +499,27 @@ def test_engine_limits_against_oracle(sts, oracle, test, prm):
         assert eng.layout.enabled_mask == mask == oracle.layout(oracle.make_params(test_mask=mask, **base)).enabled_mask
         pv, st, w = eng.run(raw, 1)
         compare_with_oracle(sts, oracle, eng, mask, base, raw, 1, pv, st, w)
+
+
+@pytest.mark.parametrize("n", [
+    1000008,            # n/2 = 2^2 3^2 17 19 43, M = 2^20: also the golden case of the reference binary (lcg_n1000008_4)
+    7 * (1 << 17),      # M = 2^20 from 2N - 1 just below it
+    8072,               # odd log2 M (one radix-2 pass), N = 4 x 1009
+    8 * 1031,           # N = 4 x 1031, M = 2^14 (radix 4 only)
+])
+def test_dft_bluestein_path(sts, oracle, n):
+    """the DFT test on stream lengths whose half is not 5-smooth (k_dft_any.cu): N_1 and the p-value against the oracle,
+    and at n = 1000008 against the reference binary's golden values"""
+    assert sts.dft_supported(n) and not half_is_5_smooth(n)
+    streams, mask = 4, 1 << 7
+    prm = dict(n=n, block_frequency_M=16384, non_overlapping_m=9, overlapping_m=9, apen_m=10, serial_m=16,
+               linear_complexity_M=500)
+    g = load_golden("lcg_n1000008_4") if n == 1000008 else None
+    raw = golden_input(g, oracle) if g is not None else oracle.lcg_bytes(3, streams, n)
+    with sts.Engine(max_streams=streams, test_mask=mask, **prm) as eng:
+        assert eng.layout.enabled_mask == mask
+        pv, st, w = eng.run(raw, streams)
+        compare_with_oracle(sts, oracle, eng, mask, prm, raw, streams, pv, st, w)
+        if g is not None:
+            assert (st[:, eng.layout.st_off[7]] == g["dft_N1"]).all()
+            assert rel_err(pv[:, eng.layout.pv_off[7]], g["pv_7"].reshape(-1)).max() <= PV_RTOL
