@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define STSGPU_ABI_VERSION 1
+#define STSGPU_ABI_VERSION 2
 
 /* test numbers: identical to enum test, defs.h:217-236 */
 enum {
@@ -98,7 +98,16 @@ typedef struct stsgpu_params {
 	int32_t apen_m;			/* tp.approximateEntropyBlockLength  (10) */
 	int32_t serial_m;		/* tp.serialBlockLength              (16) */
 	int64_t linear_complexity_M;	/* tp.linearComplexitySequenceLength (500) */
+	uint32_t flags;			/* STSGPU_FLAG_*; 0 by default */
+	uint32_t reserved;		/* must be 0 */
 } stsgpu_params;
+
+/*
+ * state->resultstxtFlag (-s, defs.h:396): also produce what the private stats structs of the 15 tests hold beyond
+ * the integers and the p-values: the floating point intermediates (`fstats`, below) and the visit
+ * counts of the LAST excursion cycle that RandomExcursions prints (randomExcursions.c:386, :860-866).
+ */
+#define STSGPU_FLAG_STATS 1u
 
 /* per-stream record layout; offsets are in elements of the respective array */
 typedef struct stsgpu_layout {
@@ -110,6 +119,8 @@ typedef struct stsgpu_layout {
 	int32_t universal_L;		/* L chosen by the rule of universal.c:145-178 */
 	int32_t pv_off[STSGPU_NUMOFTESTS + 1], pv_cnt[STSGPU_NUMOFTESTS + 1];
 	int32_t st_off[STSGPU_NUMOFTESTS + 1], st_cnt[STSGPU_NUMOFTESTS + 1];
+	int32_t nfs;			/* double statistics per stream (produced with STSGPU_FLAG_STATS only) */
+	int32_t fs_off[STSGPU_NUMOFTESTS + 1], fs_cnt[STSGPU_NUMOFTESTS + 1];
 } stsgpu_layout;
 
 /*
@@ -127,10 +138,28 @@ typedef struct stsgpu_layout {
  *  APEN             [0] bits of phi(m), [1] bits of phi(m+1), [2] sum C_m[i]^2,
  *                   [3] sum C_{m+1}[i]^2, [4] sum i*C_m[i], [5] sum i*C_{m+1}[i]
  *                                                                    (approximateEntropy.c:369-407)
- *  RND_EXCURSION    [0] J, [1 + 8*k + i] v[k][i], k = 0..5, i = 0..7 (randomExcursions.c:324-464)
+ *  RND_EXCURSION    [0] J, [1 + 8*k + i] v[k][i], k = 0..5, i = 0..7 (randomExcursions.c:324-464);
+ *                   [49 + i] visits to state i during the last cycle (stat.counter[], :386 and :441; zero
+ *                   when the test was not possible, :581) - only with STSGPU_FLAG_STATS, otherwise 0
  *  RND_EXCURSION_VAR [0] J, [1 + i] xi(state i), i = 0..17           (randomExcursionsVariant.c:262-306)
  *  SERIAL           [0..2] sum v_i^2 for block sizes m, m-1, m-2     (serial.c:390-419)
  *  LINEARCOMPLEXITY [0..6] v[class]                                  (linearComplexity.c:367-377)
+ *
+ * fstats slots, relative to fs_off[test] (the doubles of each test's private stats struct, evaluated by the tail
+ * kernels with the reference's expressions on the way to the p-value):
+ *  BLOCK_FREQUENCY  [0] chi_squared                                  (blockFrequency.c:241)
+ *  RUNS             [0] pi, [1] erfc_arg; both 0.0 (UNSET_DOUBLE) when the test is not possible (runs.c:219, :244, :299-301)
+ *  LONGEST_RUN      [0] chi2                                         (longestRunOfOnes.c:412-416)
+ *  RANK             [0] chi_squared                                  (rank.c:333-341)
+ *  DFT              [0] N_0, [1] d                                   (discreteFourierTransform.c:401, :416)
+ *  NON_OVERLAPPING  [t] chi2 of template t                           (nonOverlappingTemplateMatchings.c:561-565)
+ *  OVERLAPPING      [0] chi2                                         (overlappingTemplateMatchings.c:301-305)
+ *  UNIVERSAL        [0] sigma, [1] f_n                               (universal.c:380-386)
+ *  APEN             [0] ApEn, [1] chi_squared                        (approximateEntropy.c:222-223)
+ *  RND_EXCURSION    [i] chi2 of state i; 0.0 when the test is not possible (randomExcursions.c:492-497)
+ *  SERIAL           [0] psim0, [1] psim1, [2] psim2, [3] del1, [4] del2 (serial.c:210-218)
+ *  LINEARCOMPLEXITY [0] chi2                                         (linearComplexity.c:383-386)
+ *  FREQUENCY, CUSUM, RND_EXCURSION_VAR: none
  */
 
 typedef struct stsgpu_ctx stsgpu_ctx;
@@ -223,6 +252,12 @@ int stsgpu_pending(const stsgpu_ctx *ctx);
 int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first_iteration,
 		   const double **pvals, const int64_t **istats, const uint32_t **wcount);
 
+/*
+ * The double statistics (`fstats`, nstreams*nfs, layout.fs_off) of the same batch; *fstats is NULL when the engine
+ * was created without STSGPU_FLAG_STATS.
+ */
+int stsgpu_results_stats(stsgpu_ctx *ctx, const double **fstats);
+
 /* ---- synthetic input: tools/generators.c LCG, generator 1 ----------------------- */
 
 /*
@@ -252,10 +287,20 @@ void stsgpu_host_free(void *p);
 int stsgpu_comm_unique_id(uint8_t id[STSGPU_UNIQUE_ID_BYTES]);
 int stsgpu_comm_init(stsgpu_ctx *ctx, const uint8_t id[STSGPU_UNIQUE_ID_BYTES], int rank, int nranks);
 /*
- * Gather the p-values of the last completed batch of every rank to `root`, rank-major (rank r's
- * streams follow rank r-1's: the reference's -j job order, utilities.c:1526).  Every rank must
- * have completed a batch of the same nstreams.  On root, *pvals_all points to
- * nranks*nstreams*npv doubles in engine-owned pinned memory; elsewhere it is NULL.
+ * Gather mode: from now on every batch this context submits ends with the exchange of its p-value records to
+ * `root` (grouped ncclSend / ncclRecv queued behind the batch's tail kernels, then the copy to the root's pinned
+ * memory), so the exchange overlaps the kernels of the next batches and stsgpu_wait returns with the gathered array
+ * already on the root's host - no separate blocking call per batch.  All ranks must submit the same sequence of
+ * batches; "-F a" batches are refused in this mode.  Needs an idle engine and stsgpu_comm_init.
+ */
+int stsgpu_gather_begin(stsgpu_ctx *ctx, int root);
+/*
+ * The p-values of the last completed batch of every rank on `root`, rank-major (rank r's streams follow rank
+ * r-1's: the reference's -j job order, utilities.c:1526).  In gather mode this only hands out the array that
+ * arrived with the batch; otherwise it performs one blocking exchange (collective: every rank calls it, before
+ * submitting again into the slot of that batch).  On root, *pvals_all points to nranks*nstreams*npv doubles in
+ * engine-owned pinned memory, valid until the batch's slot is waited for again; elsewhere it is NULL.  The ranks'
+ * batch sizes travel with the data: STSGPU_E_STATE (never a hang) when a rank's batch had another nstreams.
  */
 int stsgpu_gather_pvals(stsgpu_ctx *ctx, int root, const double **pvals_all);
 int stsgpu_comm_barrier(stsgpu_ctx *ctx);
@@ -291,7 +336,9 @@ int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t uniformity_bins, double alpha, 
  * Value i lands in column pv_off[test] + (first_index + i) mod pv_cnt[test].  Synchronous.
  */
 int stsgpu_assess_add(stsgpu_ctx *ctx, int test, const double *pvals, int64_t count, int64_t first_index);
-/* sum the tallies of all ranks of the communicator into every rank (NCCL all-reduce); no-op for one rank */
+/* sum the tallies of all ranks of the communicator into every rank (NCCL all-reduce, in place); no-op for one rank
+ * and when already reduced; afterwards stsgpu_submit* / stsgpu_assess_add fail with STSGPU_E_STATE until the next
+ * stsgpu_assess_begin (the tallies would otherwise count the other ranks' share again at the next reduce) */
 int stsgpu_assess_reduce(stsgpu_ctx *ctx);
 /*
  * Verdicts of everything tallied since stsgpu_assess_begin: metrics[npv] in record order, and, if freq

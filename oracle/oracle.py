@@ -16,7 +16,7 @@ NON_P_VALUE = -99999999.0
 
 
 class Params(C.Structure):
-    _fields_ = [("n", C.c_int64), ("test_mask", C.c_uint32), ("pad", C.c_int32),
+    _fields_ = [("n", C.c_int64), ("test_mask", C.c_uint32), ("flags", C.c_int32),
                 ("block_frequency_M", C.c_int64), ("non_overlapping_m", C.c_int32),
                 ("overlapping_m", C.c_int32), ("apen_m", C.c_int32), ("serial_m", C.c_int32),
                 ("linear_complexity_M", C.c_int64)]
@@ -60,8 +60,8 @@ def lib():
 
 
 def make_params(n=1 << 20, test_mask=ALL_TESTS, block_frequency_M=16384, non_overlapping_m=9,
-                overlapping_m=9, apen_m=10, serial_m=16, linear_complexity_M=500):
-    return Params(n, test_mask, 0, block_frequency_M, non_overlapping_m, overlapping_m, apen_m, serial_m,
+                overlapping_m=9, apen_m=10, serial_m=16, linear_complexity_M=500, flags=0):
+    return Params(n, test_mask, flags, block_frequency_M, non_overlapping_m, overlapping_m, apen_m, serial_m,
                   linear_complexity_M)
 
 

@@ -187,7 +187,7 @@ oracle_layout_for(const oracle_params *p, oracle_layout *o)
 
 	const int pvc[16] = { 0, 1, 1, 2, 1, 1, 1, 1, o->ntemplates, 1, 1, 1, 8, 18, 2, 1 };
 	int bfN = (p->block_frequency_M > 0) ? (int) (n / p->block_frequency_M) : 0;
-	const int stc[16] = { 0, 1, 1 + bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 49, 19, 3, 7 };
+	const int stc[16] = { 0, 1, 1 + bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 57, 19, 3, 7 };
 	int po = 0, so = 0;
 	for (int t = 1; t <= 15; t++) {
 		if (!(en & (1u << t)))
@@ -650,7 +650,7 @@ t_rnd_excursion(const oconst *c, oscratch *s, const unsigned char *e, double *pv
 	long n = c->p.n, *S = s->S, J = 0;
 	long v[6][8];
 	memset(v, 0, sizeof(v));
-	memset(st, 0, 49 * sizeof(int64_t));
+	memset(st, 0, 57 * sizeof(int64_t));
 	S[0] = e[0] ? 1 : -1;
 	for (long i = 1; i < n; i++)
 		S[i] = S[i - 1] + (e[i] ? 1 : -1);
@@ -683,7 +683,9 @@ t_rnd_excursion(const oconst *c, oscratch *s, const unsigned char *e, double *pv
 		for (int x = 0; x < 8; x++)
 			st[1 + 8 * k + x] = v[k][x];
 	if (J < c->min_zero_crossings)
-		return;
+		return;			/* stat.counter[] is cleared in this case (:581) */
+	for (int x = 0; (c->p.flags & 1) && x < 8; x++)	/* stat.counter[] after the loop: the LAST cycle's visits (:386, :860-866) */
+		st[49 + x] = counter[x];
 	for (int i = 0; i < 8; i++) {
 		long x = (i < 4) ? (i - 4) : (i - 3);
 		long ax = labs(x);

@@ -19,7 +19,7 @@
 typedef struct oracle_params {
 	int64_t n;			/* tp.n */
 	uint32_t test_mask;		/* bit t = test t enabled */
-	int32_t pad;
+	int32_t flags;			/* 1: also report RandomExcursions' stat.counter[] (istats 49..56), like STSGPU_FLAG_STATS */
 	int64_t block_frequency_M;
 	int32_t non_overlapping_m;
 	int32_t overlapping_m;

@@ -11,7 +11,8 @@ _LIBNAME = os.environ.get("STSGPU_LIB") or os.path.join(_HERE, "libstsgpu.so")	#
 
 ALL_TESTS = 0xFFFE
 NON_P_VALUE = -99999999.0
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_STATS = 1
 UNIQUE_ID_BYTES = 128
 TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "LongestRun", "Rank", "DFT",
               "NonOverlappingTemplate", "OverlappingTemplate", "Universal", "ApproximateEntropy",
@@ -19,9 +20,9 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
 EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_query_layout", "stsgpu_dft_supported", "stsgpu_submit",
-           "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_generate_lcg",
+           "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_results_stats", "stsgpu_generate_lcg",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
-           "stsgpu_comm_init", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
+           "stsgpu_comm_init", "stsgpu_gather_begin", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
            "stsgpu_assess_add", "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
            "stsgpu_kernel_count", "stsgpu_kernel_info", "stsgpu_last_batch_ms", "stsgpu_launch_count",
            "stsgpu_debug_pattern_histogram", "stsgpu_strerror", "stsgpu_last_error", "stsgpu_abi_version"]
@@ -35,7 +36,8 @@ class Params(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n", C.c_int64), ("max_streams", C.c_int64),
                 ("test_mask", C.c_uint32), ("pipeline_depth", C.c_int32), ("block_frequency_M", C.c_int64),
                 ("non_overlapping_m", C.c_int32), ("overlapping_m", C.c_int32), ("apen_m", C.c_int32),
-                ("serial_m", C.c_int32), ("linear_complexity_M", C.c_int64)]
+                ("serial_m", C.c_int32), ("linear_complexity_M", C.c_int64), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Metric(C.Structure):
@@ -48,7 +50,8 @@ class Layout(C.Structure):
     _fields_ = [("enabled_mask", C.c_uint32), ("npv", C.c_int32), ("nst", C.c_int32), ("nw", C.c_int32),
                 ("ntemplates", C.c_int32), ("universal_L", C.c_int32),
                 ("pv_off", C.c_int32 * 16), ("pv_cnt", C.c_int32 * 16),
-                ("st_off", C.c_int32 * 16), ("st_cnt", C.c_int32 * 16)]
+                ("st_off", C.c_int32 * 16), ("st_cnt", C.c_int32 * 16),
+                ("nfs", C.c_int32), ("fs_off", C.c_int32 * 16), ("fs_cnt", C.c_int32 * 16)]
 
 
 def library_path():
@@ -94,6 +97,7 @@ def load_library():
     lib.stsgpu_wait.argtypes = [vp]
     lib.stsgpu_pending.argtypes = [vp]
     lib.stsgpu_results.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.stsgpu_results_stats.argtypes = [vp, C.POINTER(vp)]
     lib.stsgpu_generate_lcg.argtypes = [vp, i64, i64]
     lib.stsgpu_download_input.argtypes = [vp, vp, i64]
     lib.stsgpu_host_alloc.argtypes = [C.c_size_t]
@@ -102,6 +106,7 @@ def load_library():
     lib.stsgpu_host_free.restype = None
     lib.stsgpu_comm_unique_id.argtypes = [vp]
     lib.stsgpu_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.stsgpu_gather_begin.argtypes = [vp, i32]
     lib.stsgpu_gather_pvals.argtypes = [vp, i32, C.POINTER(vp)]
     lib.stsgpu_comm_barrier.argtypes = [vp]
     lib.stsgpu_assess_begin.argtypes = [vp, i64, C.c_double, C.c_double]
@@ -255,6 +260,15 @@ class Engine:
             pva, sta, wa = pva.copy(), sta.copy(), wa.copy()
         return pva, sta, wa
 
+    def results_stats(self):
+        """fstats[nstreams, nfs] of the last completed batch (engines created with flags=FLAG_STATS), else None"""
+        ns, fs = C.c_int64(), C.c_void_p()
+        self._ck(self.lib.stsgpu_results(self.h, C.byref(ns), None, None, None, None), "results")
+        self._ck(self.lib.stsgpu_results_stats(self.h, C.byref(fs)), "results_stats")
+        if not fs.value:
+            return None
+        return np.ctypeslib.as_array(C.cast(fs, C.POINTER(C.c_double)), shape=(ns.value, self.layout.nfs)).copy()
+
     def run(self, raw, nstreams, first_iteration=0):
         self.submit(raw, nstreams, first_iteration)
         self.wait()
@@ -281,6 +295,10 @@ class Engine:
     def comm_init(self, uid, rank, nranks):
         buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
         self._ck(self.lib.stsgpu_comm_init(self.h, buf, rank, nranks), "comm_init")
+
+    def gather_begin(self, root=0):
+        """gather mode: every batch submitted from now on ends with the exchange of its p-value records to `root`"""
+        self._ck(self.lib.stsgpu_gather_begin(self.h, root), "gather_begin")
 
     def gather_pvals(self, root=0, nranks=1):
         out = C.c_void_p()

@@ -21,7 +21,9 @@ struct DevParams {
 	int64_t pitch_words;		/* words between consecutive streams (multiple of 32) */
 	int32_t npv, nst, nw;		/* record sizes */
 	int32_t pv_off[16], st_off[16];
+	int32_t nfs, fs_off[16];	/* double statistics (STSGPU_FLAG_STATS) */
 	uint32_t enabled;
+	uint32_t want_stats;		/* STSGPU_FLAG_STATS: fill fstats and the last-cycle excursion counters */
 	/* per-test parameters */
 	int64_t bf_M, bf_N;		/* block frequency */
 	int32_t lr_M, lr_min_class, lr_max_class; int64_t lr_N;	/* longest run table row */
@@ -134,12 +136,14 @@ struct LaunchCtx {
 	double *d_pv;
 	long long *d_st;
 	uint32_t *d_w;
+	double *d_fs;			/* fstats, or nullptr without STSGPU_FLAG_STATS */
 	int64_t nstreams;
 	int num_sms;
 };
 
 /* kernel launchers (one per .cu file); each returns the cudaError of its launches */
 cudaError_t launch_scan(const DevParams &P, const LaunchCtx &L);
+cudaError_t launch_last_cycle(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_blocks(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_rank(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_nonoverlapping(const DevParams &P, const LaunchCtx &L, const uint32_t *d_templates);

@@ -127,7 +127,7 @@ extern "C" const char *stsgpu_strerror(int code)
 	}
 }
 
-static char g_create_err[256];
+static thread_local char g_create_err[256];	/* stsgpu_last_error(NULL): the failure of this thread's last stsgpu_create */
 extern "C" const char *stsgpu_last_error(const stsgpu_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int stsgpu_abi_version(void) { return STSGPU_ABI_VERSION; }
 
@@ -250,12 +250,14 @@ static void compute_layout(const stsgpu_params *p, stsgpu_layout *out, std::vect
 	lay.nw = lay.ntemplates * 8;
 	const int64_t bfN = p->block_frequency_M > 0 ? n / p->block_frequency_M : 0;
 	const int pvc[16] = { 0, 1, 1, 2, 1, 1, 1, 1, lay.ntemplates, 1, 1, 1, 8, 18, 2, 1 };
-	const int stc[16] = { 0, 1, 1 + (int) bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 49, 19, 3, 7 };
+	const int stc[16] = { 0, 1, 1 + (int) bfN, 5, 3, 7, 3, 1, 0, 6, 1, 6, 57, 19, 3, 7 };
+	const int fsc[16] = { 0, 0, 1, 0, 2, 1, 1, 2, lay.ntemplates, 1, 2, 2, 8, 0, 5, 1 };
 	for (int t = 1; t <= 15; t++) {
 		if (!((en >> t) & 1u))
 			continue;
 		lay.pv_off[t] = lay.npv; lay.pv_cnt[t] = pvc[t]; lay.npv += pvc[t];
 		lay.st_off[t] = lay.nst; lay.st_cnt[t] = stc[t]; lay.nst += stc[t];
+		lay.fs_off[t] = lay.nfs; lay.fs_cnt[t] = fsc[t]; lay.nfs += fsc[t];
 	}
 }
 
@@ -268,6 +270,10 @@ static int check_params(const stsgpu_params *p, const char **why)
 	}
 	if (p->n < 8 || (p->n % 8) != 0 || p->max_streams < 1) {	/* parse_args.c:939: n must be a multiple of 8 */
 		*why = "n must be a positive multiple of 8 and max_streams >= 1";
+		return STSGPU_E_INVAL;
+	}
+	if ((p->flags & ~STSGPU_FLAG_STATS) != 0 || p->reserved != 0) {
+		*why = "unknown flag bits";
 		return STSGPU_E_INVAL;
 	}
 	if (p->n > (1LL << 31) - 4096) {
@@ -356,7 +362,9 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	P.nwords = (n + 31) / 32;
 	P.pitch_words = ((P.nwords + 4 + 31) / 32) * 32;
 	P.npv = lay.npv; P.nst = lay.nst; P.nw = lay.nw;
-	for (int t = 0; t < 16; t++) { P.pv_off[t] = lay.pv_off[t]; P.st_off[t] = lay.st_off[t]; }
+	for (int t = 0; t < 16; t++) { P.pv_off[t] = lay.pv_off[t]; P.st_off[t] = lay.st_off[t]; P.fs_off[t] = lay.fs_off[t]; }
+	P.nfs = lay.nfs;
+	P.want_stats = (p->flags & STSGPU_FLAG_STATS) ? 1u : 0u;
 	P.enabled = en;
 	P.bf_M = p->block_frequency_M; P.bf_N = bfN;
 	int idx = 0;								/* longestRunOfOnes.c:352-360 */
@@ -487,6 +495,10 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 		    "cudaMallocHost(istats)");
 		CKC(pinned_alloc_near((void **) &S.h_w, (size_t) B * (lay.nw + 1) * sizeof(uint32_t), ctx->device),
 		    "cudaMallocHost(wcount)");
+		if (P.want_stats && lay.nfs > 0) {
+			CKC(cudaMalloc((void **) &S.d_fs, (size_t) B * lay.nfs * sizeof(double)), "cudaMalloc(fstats)");
+			CKC(pinned_alloc_near((void **) &S.h_fs, (size_t) B * lay.nfs * sizeof(double), ctx->device), "cudaMallocHost(fstats)");
+		}
 		CKC(cudaMalloc((void **) &S.d_hist_flags, (size_t) B * sizeof(uint32_t)), "cudaMalloc(hist flags)");
 		if (want_apen)
 			CKC(cudaMalloc((void **) &S.d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
@@ -676,6 +688,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		Slot &S = ctx->slots[i];
 		cudaFree(S.d_in); cudaFree(S.d_pv); cudaFree(S.d_st); cudaFree(S.d_w);
 		cudaFreeHost(S.h_pv); cudaFreeHost(S.h_st); cudaFreeHost(S.h_w);
+		cudaFree(S.d_fs); cudaFreeHost(S.h_fs);
 		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags);
 		cudaFree(S.d_text); cudaFree(S.d_ascii); cudaFreeHost(S.h_ascii);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
@@ -701,6 +714,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
 	cudaFree(ctx->d_tally);
 	cudaFree(ctx->d_assess_stage);
+	cudaFree(ctx->d_metrics);
 	for (int i = 0; i < 12; i++) cudaFree(ctx->dft_tabs[i]);
 	if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
 	delete ctx;
@@ -746,7 +760,7 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	const bool prof = ctx->profiling;
 
 	LaunchCtx L;
-	L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
+	L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w; L.d_fs = S.d_fs;
 	L.nstreams = nstreams; L.num_sms = ctx->num_sms;
 	L.stream2 = S.s_dft[1]; L.ev2_fork = S.ev_dft_fork; L.ev2_join = S.ev_dft_join;
 
@@ -776,7 +790,14 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		cudaError_t e = cudaSuccess;
 		int64_t launched = 0;
 		switch (g) {
-		case G_SCAN: e = launch_scan(P, L); launched = 1; break;
+		case G_SCAN:
+			e = launch_scan(P, L);
+			launched = 1;
+			if (e == cudaSuccess && P.want_stats && (P.enabled & (1u << STSGPU_TEST_RND_EXCURSION))) {
+				e = launch_last_cycle(P, L);	/* -s only: stat.counter[] of the last cycle, after J is known */
+				launched = 2;
+			}
+			break;
 		case G_BLOCKS: e = launch_blocks(P, L); launched = 3; break;
 		case G_RANK: e = launch_rank(P, L); launched = 1; break;
 		case G_NONOV: e = launch_nonoverlapping(P, L, ctx->d_templates); launched = 1; break;
@@ -847,8 +868,18 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	CK(cudaMemcpyAsync(S.h_st, S.d_st, (size_t) nstreams * lay.nst * sizeof(long long), cudaMemcpyDeviceToHost, sl));
 	if (lay.nw)
 		CK(cudaMemcpyAsync(S.h_w, S.d_w, (size_t) nstreams * lay.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl));
+	if (S.d_fs)
+		CK(cudaMemcpyAsync(S.h_fs, S.d_fs, (size_t) nstreams * lay.nfs * sizeof(double), cudaMemcpyDeviceToHost, sl));
 	if (S.ascii)
 		CK(cudaMemcpyAsync(S.h_ascii, S.d_ascii, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl));
+	S.nstreams = nstreams;
+	S.first = first_iteration;
+	S.gathered = false;
+	if (ctx->gather_root >= 0) {
+		const int rc = stsgpu_comm_enqueue_gather(ctx, S, nstreams, sl);
+		if (rc != STSGPU_OK)
+			return rc;
+	}
 	CK(cudaEventRecord(S.ev_done, sl));
 	S.nstreams = nstreams;
 	S.first = first_iteration;
@@ -867,6 +898,10 @@ static int next_slot(stsgpu_ctx *ctx, int64_t nstreams, Slot **out)
 		return STSGPU_E_RANGE;
 	}
 	Slot &S = ctx->slots[ctx->submit_seq % ctx->nslots];
+	if (ctx->assessing && ctx->tally_reduced) {
+		snprintf(ctx->err, sizeof(ctx->err), "the tallies hold the sum over all ranks (stsgpu_assess_reduce): call stsgpu_assess_begin before the next batch");
+		return STSGPU_E_STATE;
+	}
 	if (S.in_flight) {
 		snprintf(ctx->err, sizeof(ctx->err), "%d batches are in flight (pipeline_depth): call stsgpu_wait first",
 			 ctx->nslots);
@@ -923,10 +958,14 @@ extern "C" int stsgpu_submit_ascii(stsgpu_ctx *ctx, const char *text, int64_t te
 	const int64_t cap = (ctx->prm.max_streams + 1) * n;		/* one stream of slack for white space */
 	if (text_len > cap)
 		text_len = cap;
-	if (S.d_text == nullptr) {
+	if (S.d_text == nullptr || S.d_ascii == nullptr || S.h_ascii == nullptr) {
 		if (cudaMalloc((void **) &S.d_text, (size_t) cap + 16) != cudaSuccess ||
 		    cudaMalloc((void **) &S.d_ascii, 2 * sizeof(unsigned long long)) != cudaSuccess ||
 		    cudaMallocHost((void **) &S.h_ascii, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+			/* all three or none: a later call must not find a half-made staging area */
+			cudaFree(S.d_text); cudaFree(S.d_ascii); cudaFreeHost(S.h_ascii);
+			S.d_text = nullptr; S.d_ascii = nullptr; S.h_ascii = nullptr;
+			cudaGetLastError();
 			snprintf(ctx->err, sizeof(ctx->err), "cannot allocate the %lld-byte ASCII staging buffer", (long long) cap);
 			return STSGPU_E_NOMEM;
 		}
@@ -973,10 +1012,10 @@ extern "C" int stsgpu_wait(stsgpu_ctx *ctx)
 		return STSGPU_E_STATE;
 	}
 	cudaSetDevice(ctx->device);
+	CK(cudaEventSynchronize(S.ev_done));	/* a failed wait leaves the batch pending: the pipeline state moves only on success */
+	CK(cudaGetLastError());
 	S.in_flight = false;
 	ctx->wait_seq++;
-	CK(cudaEventSynchronize(S.ev_done));
-	CK(cudaGetLastError());
 	if (S.ascii && S.h_ascii[0] < (unsigned long long) S.nstreams)
 		S.nstreams = (int64_t) S.h_ascii[0];		/* the text ended inside stream h_ascii[0] */
 	ctx->last_done = idx;
@@ -1007,6 +1046,18 @@ extern "C" int stsgpu_results(stsgpu_ctx *ctx, int64_t *nstreams, int64_t *first
 	if (pvals) *pvals = S.h_pv;
 	if (istats) *istats = (const int64_t *) S.h_st;
 	if (wcount) *wcount = S.h_w;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_results_stats(stsgpu_ctx *ctx, const double **fstats)
+{
+	if (ctx == NULL || fstats == NULL)
+		return STSGPU_E_INVAL;
+	if (!ctx->have_results) {
+		snprintf(ctx->err, sizeof(ctx->err), "no completed batch");
+		return STSGPU_E_STATE;
+	}
+	*fstats = ctx->slots[ctx->last_done].h_fs;	/* NULL without STSGPU_FLAG_STATS */
 	return STSGPU_OK;
 }
 
@@ -1072,6 +1123,7 @@ extern "C" int stsgpu_assess_begin(stsgpu_ctx *ctx, int64_t bins, double alpha, 
 	ctx->assess_alpha = alpha;
 	ctx->assess_level = level;
 	ctx->assessing = true;
+	ctx->tally_reduced = false;
 	return STSGPU_OK;
 }
 
@@ -1083,6 +1135,10 @@ extern "C" int stsgpu_assess_add(stsgpu_ctx *ctx, int test, const double *pvals,
 		return STSGPU_E_INVAL;
 	if (!ctx->assessing || ctx->submit_seq != ctx->wait_seq) {
 		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_assess_add needs stsgpu_assess_begin and an idle engine");
+		return STSGPU_E_STATE;
+	}
+	if (ctx->tally_reduced) {
+		snprintf(ctx->err, sizeof(ctx->err), "the tallies hold the sum over all ranks (stsgpu_assess_reduce): call stsgpu_assess_begin before adding more");
 		return STSGPU_E_STATE;
 	}
 	if (!((ctx->lay.enabled_mask >> test) & 1u)) {
@@ -1121,8 +1177,9 @@ extern "C" int stsgpu_assess_finish(stsgpu_ctx *ctx, stsgpu_metric *metrics, int
 		return STSGPU_E_CUDA;
 	const int npv = ctx->lay.npv;
 	const int64_t bins = ctx->assess_bins;
-	stsgpu_metric *d_out = nullptr;
-	CK(cudaMalloc((void **) &d_out, (size_t) npv * sizeof(stsgpu_metric)));
+	if (ctx->d_metrics == nullptr)
+		CK(cudaMalloc((void **) &ctx->d_metrics, (size_t) npv * sizeof(stsgpu_metric)));
+	stsgpu_metric *d_out = ctx->d_metrics;
 	/* lgamma of the per-run constant (bins - 1) / 2 with glibc, like every other tail constant */
 	cudaError_t e = launch_assess_finish(ctx->P, bins, ctx->assess_alpha, ctx->assess_level, lgamma((bins - 1.0) / 2.0),
 					     ctx->d_tally, d_out, ctx->s_main);
@@ -1130,7 +1187,6 @@ extern "C" int stsgpu_assess_finish(stsgpu_ctx *ctx, stsgpu_metric *metrics, int
 		e = cudaMemcpyAsync(metrics, d_out, (size_t) npv * sizeof(stsgpu_metric), cudaMemcpyDeviceToHost, ctx->s_main);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(ctx->s_main);
-	cudaFree(d_out);
 	if (e != cudaSuccess) {
 		set_err(ctx, "assess finish", e);
 		return STSGPU_E_CUDA;
@@ -1195,7 +1251,7 @@ extern "C" int stsgpu_debug_pattern_histogram(stsgpu_ctx *ctx, int64_t s, int bi
 		CK(cudaMalloc((void **) &ctx->d_debug, sizeof(uint32_t) << 21));
 	LaunchCtx L;
 	L.stream2 = nullptr; L.ev2_fork = L.ev2_join = nullptr;
-	L.stream = ctx->s_main; L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w;
+	L.stream = ctx->s_main; L.d_in = S.d_in; L.d_pv = S.d_pv; L.d_st = S.d_st; L.d_w = S.d_w; L.d_fs = nullptr;
 	L.nstreams = 1; L.num_sms = ctx->num_sms;
 	cudaError_t e = launch_debug_histogram(ctx->P, L, s, bits, ctx->d_debug);
 	if (e != cudaSuccess) {

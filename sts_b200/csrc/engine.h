@@ -24,6 +24,11 @@ struct Slot {
 	double *h_pv = nullptr;
 	long long *h_st = nullptr;
 	uint32_t *h_w = nullptr;
+	double *d_fs = nullptr, *h_fs = nullptr;	/* fstats (STSGPU_FLAG_STATS) */
+	/* gather mode (comm.cu): this batch's records of every rank, on the root; {nstreams} of this rank's batch */
+	double *d_gather = nullptr, *h_gather = nullptr;
+	double *d_hdr = nullptr, *h_hdr = nullptr, *d_hdr_all = nullptr, *h_hdr_all = nullptr;
+	bool gathered = false;
 	uint32_t *d_apen_hist = nullptr;
 	uint32_t *d_hist_flags = nullptr;	/* streams the packed 16-bit histogram could not count exactly */
 	double2 *d_dft_work = nullptr;
@@ -78,6 +83,7 @@ struct stsgpu_ctx {
 	int64_t assess_bins = 0;
 	double assess_alpha = 0.01, assess_level = 0.0001;
 	unsigned long long *d_tally = nullptr;
+	stsgpu_metric *d_metrics = nullptr;	/* stsgpu_assess_finish: verdicts, one per p-value column */
 	double *d_assess_stage = nullptr;	/* stsgpu_assess_add: staging for p-values read from files */
 
 	bool profiling = false;
@@ -86,13 +92,16 @@ struct stsgpu_ctx {
 	/* NCCL (comm.cu) */
 	void *nccl_comm = nullptr;
 	int rank = 0, nranks = 1;
-	double *d_gather = nullptr, *h_gather = nullptr;
-	size_t gather_cap = 0;
+	double *d_gather = nullptr;	/* stsgpu_comm_barrier's word */
+	int gather_root = -1;		/* >= 0: gather mode, every batch ends with the exchange (stsgpu_gather_begin) */
+	bool tally_reduced = false;	/* the tallies already hold the sum over ranks (stsgpu_assess_reduce) */
 
 	char err[256] = { 0 };
 };
 
 void stsgpu_comm_destroy_internal(stsgpu_ctx *ctx);
+/* gather mode: queue this batch's exchange on `stream` after its tails (comm.cu); no-op outside gather mode */
+int stsgpu_comm_enqueue_gather(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, cudaStream_t stream);
 
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
 			 cudaStream_t s_cusum, cudaStream_t s_apen);

@@ -394,3 +394,135 @@ cudaError_t launch_scan(const DevParams &P, const LaunchCtx &L)
 	scan_kernel<<<(unsigned) L.nstreams, SCAN_THREADS, 0, L.stream>>>(P, L.d_in, L.d_st, L.nstreams);
 	return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * -s only (STSGPU_FLAG_STATS): stat.counter[] of RandomExcursions as its stats.txt prints it - the visit counts of
+ * the LAST cycle alone, because the reference clears the counters at the start of every cycle
+ * (randomExcursions.c:386) and prints what is left after the loop (:860-866); zero when the test was not possible
+ * (:581).  With the cycle ends E = { i in [1, n-1] : S_i = 0 } plus n if S_(n-1) != 0 (:337-347), the last cycle is
+ * i in [z2, z1) for the two largest elements z1 > z2 of E (z2 = 0 when E has one element, :378), and counter[x]
+ * = #{ i in [z2, z1) : S_i = x } for x in -4..-1, 1..4, not saturated.
+ *
+ * One CTA per stream, thread t owns a contiguous run of words: local sums -> block scan = walk value at the start
+ * of every run; one walk to find each thread's last two zeros, a second one to count inside [z2, z1).  Words that
+ * cannot come within reach of the levels of interest are skipped by their popcount.  Runs after scan_kernel on
+ * the same stream (J is read from the record).
+ */
+#define LASTC_THREADS 256
+
+__global__ void __launch_bounds__(LASTC_THREADS)
+last_cycle_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st, int64_t nstreams)
+{
+	__shared__ int warp_tot[LASTC_THREADS / 32];
+	__shared__ long long zero_a[LASTC_THREADS], zero_b[LASTC_THREADS];
+	__shared__ long long range[2];
+	__shared__ unsigned long long counter[8];
+	const int64_t s = blockIdx.x;
+	if (s >= nstreams)
+		return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t n = P.n, nwords = P.nwords;
+	long long *c = st + s * P.nst + P.st_off[STSGPU_TEST_RND_EXCURSION];
+	if (tid < 8)
+		counter[tid] = 0;
+	const int64_t per = (nwords + LASTC_THREADS - 1) / LASTC_THREADS;
+	const int64_t w0 = min(nwords, (int64_t) tid * per), w1 = min(nwords, w0 + per);
+
+	int loc = 0;
+	for (int64_t i = w0; i < w1; i++) {
+		const int64_t rem = n - i * 32;
+		loc += 2 * __popc(ldw(w, i)) - (int) (rem >= 32 ? 32 : rem);
+	}
+	const int incl = warp_scan_incl(loc, lane);
+	if (lane == 31)
+		warp_tot[warp] = incl;
+	__syncthreads();
+	int S_run = incl - loc, S_total = 0;
+	for (int j = 0; j < LASTC_THREADS / 32; j++) {
+		if (j < warp)
+			S_run += warp_tot[j];
+		S_total += warp_tot[j];
+	}
+
+	/* the last two zeros of this thread's run (0 = none: position 0 is never a zero, and it is where the first cycle starts) */
+	long long za = 0, zb = 0;
+	{
+		int S = S_run;
+		for (int64_t i = w0; i < w1; i++) {
+			const uint32_t wd = ldw(w, i);
+			const int64_t rem = n - i * 32;
+			const int vb = (int) (rem >= 32 ? 32 : rem);
+			if (abs(S) <= vb) {
+				int Sx = S;
+				for (int p = 0; p < vb; p++) {
+					Sx += ((wd >> (31 - p)) & 1u) ? 1 : -1;
+					const long long pos = i * 32 + p;
+					if (Sx == 0 && pos <= n - 1) {
+						zb = za;
+						za = pos;
+					}
+				}
+			}
+			S += 2 * __popc(wd) - vb;
+		}
+	}
+	zero_a[tid] = za;
+	zero_b[tid] = zb;
+	__syncthreads();
+	if (tid == 0) {
+		long long top[2] = { 0, 0 };
+		int found = 0;
+		for (int t = LASTC_THREADS - 1; t >= 0 && found < 2; t--) {
+			if (zero_a[t] > 0 && found < 2) top[found++] = zero_a[t];
+			if (zero_b[t] > 0 && found < 2) top[found++] = zero_b[t];
+		}
+		/* S_(n-1) != 0: the trailing partial cycle [last zero, n); else the cycle that ends at the zero n - 1 */
+		if (S_total != 0) {
+			range[1] = n;
+			range[0] = top[0];
+		} else {
+			range[1] = top[0];
+			range[0] = top[1];
+		}
+	}
+	__syncthreads();
+	const long long z2 = range[0], z1 = range[1];
+	const bool possible = c[0] >= P.min_zero_crossings;
+	if (possible) {
+		unsigned int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+		int S = S_run;
+		for (int64_t i = w0; i < w1; i++) {
+			const uint32_t wd = ldw(w, i);
+			const int64_t rem = n - i * 32;
+			const int vb = (int) (rem >= 32 ? 32 : rem);
+			const long long b0 = i * 32;
+			if (b0 + vb > z2 && b0 < z1 && abs(S) <= vb + 4) {
+				int Sx = S;
+				for (int p = 0; p < vb; p++) {
+					Sx += ((wd >> (31 - p)) & 1u) ? 1 : -1;
+					const long long pos = b0 + p;
+					if (pos >= z2 && pos < z1 && Sx != 0 && abs(Sx) <= 4)
+						cnt[Sx < 0 ? Sx + 4 : Sx + 3]++;
+				}
+			}
+			S += 2 * __popc(wd) - vb;
+		}
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			const unsigned int v = (unsigned int) warp_sum((int) cnt[x]);
+			if (lane == 0 && v)
+				atomicAdd(&counter[x], (unsigned long long) v);
+		}
+	}
+	__syncthreads();
+	if (tid < 8)
+		c[49 + tid] = possible ? (long long) counter[tid] : 0;
+}
+
+cudaError_t launch_last_cycle(const DevParams &P, const LaunchCtx &L)
+{
+	last_cycle_kernel<<<(unsigned) L.nstreams, LASTC_THREADS, 0, L.stream>>>(P, L.d_in, L.d_st, L.nstreams);
+	return cudaGetLastError();
+}

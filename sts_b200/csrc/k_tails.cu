@@ -122,7 +122,7 @@ __device__ __forceinline__ int test_of_slot(const DevParams &P, int q, int *sub)
 
 __global__ void __launch_bounds__(TAIL_THREADS)
 tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ w_all,
-		   double *__restrict__ pv_all, int64_t nstreams)
+		   double *__restrict__ pv_all, double *__restrict__ fs_all, int64_t nstreams)
 {
 	/* warp -> (slot q, 32 consecutive streams) */
 	const int64_t groups = (nstreams + 31) >> 5;
@@ -139,6 +139,8 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 		int sub;
 		const int t = test_of_slot(P, q, &sub);
 		const long long *c = st + P.st_off[t];
+		/* -s: the doubles of the test's private stats struct (include/stsgpu.h, fstats) */
+		double *fs = fs_all ? fs_all + s * P.nfs + P.fs_off[t] : nullptr;
 		double p = 0.0;
 		bool write = true;
 		switch (t) {
@@ -157,6 +159,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 				sum += v * v;
 			}
 			double chi_squared = 4.0 * M * sum;
+			if (fs) fs[0] = chi_squared;
 			p = d_igamc(N / 2.0, chi_squared / 2.0, K.lgam_bf);
 			break;
 		}
@@ -169,8 +172,10 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 				double erfc_arg = fabs(V_n - 2.0 * (double) n * pi * (1.0 - pi)) /
 						  (2.0 * pi * (1.0 - pi) * K.sqrt2n);
 				p = erfc(erfc_arg);
+				if (fs) { fs[0] = pi; fs[1] = erfc_arg; }
 			} else {
 				p = NONP;
+				if (fs) { fs[0] = 0.0; fs[1] = 0.0; }	/* UNSET_DOUBLE, runs.c:299-301 */
 			}
 			break;
 		}
@@ -181,6 +186,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 				double chi_term = c[i] - (N * K.lr_pi[i]);
 				chi2 += chi_term * chi_term / (N * K.lr_pi[i]);
 			}
+			if (fs) fs[0] = chi2;
 			p = d_igamc(6 / 2.0, chi2 / 2.0, K.lgam_3);
 			break;
 		}
@@ -191,12 +197,14 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 			double chi = (((F_M - mc * K.p_32) * (F_M - mc * K.p_32) / (mc * K.p_32)) +
 				      ((F_M1 - mc * K.p_31) * (F_M1 - mc * K.p_31) / (mc * K.p_31)) +
 				      ((F_rem - mc * K.p_30) * (F_rem - mc * K.p_30) / (mc * K.p_30)));
+			if (fs) fs[0] = chi;
 			p = exp(-chi / 2.0);
 			break;
 		}
 		case STSGPU_TEST_DFT: {				/* discreteFourierTransform.c:401-423 */
 			double N_0 = (double) 0.95 * n / 2.0;
 			double d = (c[0] - N_0) / K.sqrtn4_095_005;
+			if (fs) { fs[0] = N_0; fs[1] = d; }
 			p = erfc(fabs(d) / K.sqrt2);
 			break;
 		}
@@ -206,6 +214,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 				double chi2_term = ((double) wc[sub * 8 + i] - K.nonov_mu) / K.nonov_sqrt_sigma2;
 				chi2 += (chi2_term * chi2_term);
 			}
+			if (fs) fs[sub] = chi2;
 			p = d_igamc(8 / 2.0, chi2 / 2.0, K.lgam_4);
 			break;
 		}
@@ -216,12 +225,14 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 				double chi2_term = (double) c[i] - (double) N * K.ov_pi[i];
 				chi2 += chi2_term * chi2_term / ((double) N * K.ov_pi[i]);
 			}
+			if (fs) fs[0] = chi2;
 			p = d_igamc(5 / 2.0, chi2 / 2.0, K.lgam_2_5);
 			break;
 		}
 		case STSGPU_TEST_UNIVERSAL: {			/* universal.c:380-390 */
 			double sum = __longlong_as_double(c[0]);
 			double f_n = (sum / (double) P.univ_K);
+			if (fs) { fs[0] = K.univ_sigma; fs[1] = f_n; }
 			double arg = fabs(f_n - K.univ_expected) / (K.sqrt2 * K.univ_sigma);
 			p = erfc(arg);
 			break;
@@ -230,6 +241,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 			const long long J = c[0];
 			if (J < P.min_zero_crossings) {
 				p = NONP;
+				if (fs) fs[sub] = 0.0;
 			} else {
 				int x = (sub < 4) ? (sub - 4) : (sub - 3);
 				int ax = x < 0 ? -x : x;
@@ -238,6 +250,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 					double sum_term = (double) c[1 + 8 * j + sub] - ((double) J * K.rex_pi[ax - 1][j]);
 					chi2 += sum_term * sum_term / ((double) J * K.rex_pi[ax - 1][j]);
 				}
+				if (fs) fs[sub] = chi2;
 				p = d_igamc((double) (6 - 1) / 2.0, chi2 / 2.0, K.lgam_2_5);
 			}
 			break;
@@ -269,6 +282,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 			}
 			double del1 = psi[0] - psi[1];
 			double del2 = psi[0] - 2.0 * psi[1] + psi[2];
+			if (fs && sub == 0) { fs[0] = psi[0]; fs[1] = psi[1]; fs[2] = psi[2]; fs[3] = del1; fs[4] = del2; }
 			if (sub == 0)
 				p = d_igamc((double) ((long long) 1 << (m - 1)) / 2.0, del1 / 2.0, K.lgam_serial1);
 			else
@@ -280,6 +294,7 @@ tails_slots_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, co
 			double chi2 = 0.0;
 			for (int i = 0; i < 7; i++)
 				chi2 += (c[i] - N * K.lc_pi[i]) * (c[i] - N * K.lc_pi[i]) / (N * K.lc_pi[i]);
+			if (fs) fs[0] = chi2;
 			p = d_igamc(6 / 2.0, chi2 / 2.0, K.lgam_3);
 			break;
 		}
@@ -349,7 +364,7 @@ tails_cusum_kernel(DevParams P, TailConsts K, const long long *__restrict__ st_a
 /* ApproximateEntropy, approximateEntropy.c:396-407 and :230-246: one warp per stream */
 __global__ void __launch_bounds__(TAIL_THREADS)
 tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, const uint32_t *__restrict__ apen_hist,
-		  double *__restrict__ pv_all, int64_t nstreams)
+		  double *__restrict__ pv_all, double *__restrict__ fs_all, int64_t nstreams)
 {
 	__shared__ __align__(16) double tbuf[TAIL_THREADS / 32][128];
 	const int64_t s = (int64_t) blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
@@ -391,7 +406,7 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
 					mag += tb[j];
 			}
 		}
-		phi[r] = -mag / (double) n;
+		phi[r] = (mag == 0.0) ? 0.0 : -mag / (double) n;	/* the reference's sum of non-positive terms is +0.0, not -0.0, when every term is zero */
 	}
 	if (lane == 0) {
 		long long *c = st + P.st_off[STSGPU_TEST_APEN];
@@ -399,6 +414,11 @@ tails_apen_kernel(DevParams P, TailConsts K, long long *__restrict__ st_all, con
 		c[1] = __double_as_longlong(phi[1]);
 		double ApEn = phi[0] - phi[1];
 		double chi_squared = 2.0 * n * (K.log2_ - ApEn);
+		if (fs_all) {
+			double *fs = fs_all + s * P.nfs + P.fs_off[STSGPU_TEST_APEN];
+			fs[0] = ApEn;
+			fs[1] = chi_squared;
+		}
 		pv[P.pv_off[STSGPU_TEST_APEN]] = d_igamc((double) ((long long) 1 << (m - 1)), chi_squared / 2.0, K.lgam_apen);
 	}
 }
@@ -531,12 +551,12 @@ cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCt
 	const int64_t groups = (L.nstreams + 31) >> 5;
 	const int64_t slot_warps = groups * P.npv;
 	tails_slots_kernel<<<(unsigned) ((slot_warps + wpb - 1) / wpb), TAIL_THREADS, 0, L.stream>>>(P, K, L.d_st, L.d_w, L.d_pv,
-												      L.nstreams);
+												      L.d_fs, L.nstreams);
 	if (P.enabled & (1u << STSGPU_TEST_CUSUM))
 		tails_cusum_kernel<<<(unsigned) ((2 * L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, s_cusum>>>(P, K, L.d_st, L.d_pv,
 														 L.nstreams);
 	if (P.enabled & (1u << STSGPU_TEST_APEN))
 		tails_apen_kernel<<<(unsigned) ((L.nstreams + wpb - 1) / wpb), TAIL_THREADS, 0, s_apen>>>(P, K, L.d_st, d_apen_hist,
-													   L.d_pv, L.nstreams);
+													   L.d_pv, L.d_fs, L.nstreams);
 	return cudaGetLastError();
 }

@@ -371,9 +371,10 @@ read_parallel(struct sts_state *s, uint8_t *dst, size_t len, off_t off)
 	if (len < ((size_t) 8 << 20))
 		nt = 1;
 	struct read_slice sl[64];
-	const size_t per = ((len / (size_t) nt) + 4095) & ~(size_t) 4095;
+	/* ceil(len / nt) rounded up to 4 KiB: at most nt slices, whatever len is */
+	const size_t per = (((len + (size_t) nt - 1) / (size_t) nt) + 4095) & ~(size_t) 4095;
 	int used = 0;
-	for (size_t o = 0; o < len; o += per, used++) {
+	for (size_t o = 0; o < len && used < 64; o += per, used++) {
 		sl[used].fd = fileno(s->streamFile);
 		sl[used].dst = dst + o;
 		sl[used].len = (len - o < per) ? len - o : per;

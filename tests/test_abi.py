@@ -26,13 +26,22 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libstsgpu.so does not export %s" % name
     assert sorted(binding.EXPORTS) == declared, "binding.EXPORTS out of sync with include/stsgpu.h"
-    assert lib.stsgpu_abi_version() == 1
+    assert lib.stsgpu_abi_version() == 2
 
 
-def test_struct_sizes_match_header():
-    # stsgpu_params: 2 x i32, 2 x i64, u32 + i32, i64, 4 x i32, i64  = 64 bytes; layout: 6 + 4*16 int32
-    assert ctypes.sizeof(binding.Params) == 64
-    assert ctypes.sizeof(binding.Layout) == 4 * (6 + 64)
+def test_struct_sizes_match_header(tmp_path):
+    """the ctypes mirrors against what a C compiler makes of include/stsgpu.h"""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "stsgpu.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(stsgpu_params), sizeof(stsgpu_layout), sizeof(stsgpu_metric), offsetof(stsgpu_params, flags), '
+                   'offsetof(stsgpu_layout, fs_off)); return 0; }\n')
+    exe = str(tmp_path / "sz")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(binding.Params), ctypes.sizeof(binding.Layout), ctypes.sizeof(binding.Metric),
+                     binding.Params.flags.offset, binding.Layout.fs_off.offset]
+    assert sizes[0] == 72 and sizes[1] == 4 * (6 + 64 + 1 + 32)
 
 
 def test_default_params_are_the_reference_defaults():

@@ -52,6 +52,7 @@ test_engine_matches_reference_golden_and_oracle = _pick(G.test_engine_matches_re
                                                         lambda case: case != "patterns_6")
 test_engine_config4_parameters = slow(_rebind(G.test_engine_config4_parameters, ""))
 test_full_batch_properties_and_sampled_parity = slow(_rebind(G.test_full_batch_properties_and_sampled_parity, ""))   # 1024 streams: ~2.5 min
+test_stats_flag_last_cycle_counters_and_fstats = _pick(G.test_stats_flag_last_cycle_counters_and_fstats, lambda n: True)
 test_device_lcg_is_the_reference_generator = _rebind(G.test_device_lcg_is_the_reference_generator, "")
 test_cyclic_pattern_histogram = _pick(G.test_cyclic_pattern_histogram, lambda bits: bits in (3, 16, 18))
 test_pipelined_batches_complete_in_order = _rebind(G.test_pipelined_batches_complete_in_order, "")

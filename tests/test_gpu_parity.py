@@ -117,6 +117,49 @@ def test_engine_config4_parameters(sts, oracle):
         assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("n", [1 << 20, 1000008])
+def test_stats_flag_last_cycle_counters_and_fstats(sts, oracle, n):
+    """STSGPU_FLAG_STATS (-s): the visit counts of the LAST excursion cycle (randomExcursions.c:386, :860-866)
+    bit-exact against the oracle, fstats consistent with the integers and p-values of the same record, and every other
+    column unchanged by the flag.  (That the -s files made from them equal the reference's is tests/test_integration.py.)"""
+    B = 6
+    raw = oracle.lcg_bytes(3, B, n)
+    mask = sts.ALL_TESTS & ~(1 << 7) if not half_is_5_smooth(n) else sts.ALL_TESTS
+    with sts.Engine(max_streams=B, n=n, test_mask=mask, flags=sts.FLAG_STATS) as eng:
+        pv, st, w = eng.run(raw, B)
+        fs = eng.results_stats()
+        lay = eng.layout
+    with sts.Engine(max_streams=B, n=n, test_mask=mask) as eng:
+        pv0, st0, w0 = eng.run(raw, B)
+        assert eng.results_stats() is None
+    o12 = lay.st_off[12]
+    assert (pv == pv0).all() and (w == w0).all()
+    keep = [c for c in range(lay.nst) if not (o12 + 49 <= c < o12 + 57)]
+    assert (st[:, keep] == st0[:, keep]).all() and (st0[:, o12 + 49:o12 + 57] == 0).all()
+    opv, ost, ow, olay = oracle.run(oracle.make_params(n=n, test_mask=mask, flags=1), raw, B, nthreads=os.cpu_count() or 1)
+    assert (st[:, o12 + 49:o12 + 57] == ost[:, o12 + 49:o12 + 57]).all()
+    possible = st[:, o12] >= 500
+    assert possible.any() and (st[possible, o12 + 49:o12 + 57].sum(axis=1) > 0).all()
+    assert fs.shape == (B, lay.nfs) and lay.nfs == sum(lay.fs_cnt) == 24 + lay.ntemplates + 2 * ((lay.enabled_mask >> 7) & 1)
+    # Serial: del1 = psim0 - psim1, del2 = psim0 - 2 psim1 + psim2 (serial.c:217-218)
+    f14 = fs[:, lay.fs_off[14]:lay.fs_off[14] + 5]
+    assert (f14[:, 3] == f14[:, 0] - f14[:, 1]).all() and (f14[:, 4] == f14[:, 0] - 2.0 * f14[:, 1] + f14[:, 2]).all()
+    # Runs: pi = ones / n (runs.c:219); DFT: N_0 = 0.95 n / 2; Rank: p = exp(-chi2 / 2) (rank.c:346)
+    assert (fs[:, lay.fs_off[4]] == st[:, lay.st_off[4]] / float(n)).all()
+    if (lay.enabled_mask >> 7) & 1:
+        assert (fs[:, lay.fs_off[7]] == 0.95 * n / 2.0).all()
+    assert rel_err(np.exp(-fs[:, lay.fs_off[6]] / 2.0), pv[:, lay.pv_off[6]]).max() <= 1e-12
+    # ApEn: ApEn = phi(m) - phi(m+1) (approximateEntropy.c:222)
+    phi = st[:, lay.st_off[11]:lay.st_off[11] + 2].copy().view(np.float64)
+    assert (fs[:, lay.fs_off[11]] == phi[:, 0] - phi[:, 1]).all()
+    # non-overlapping: chi2 = sum ((W - mu) / sigma)^2 per template (nonOverlappingTemplateMatchings.c:561-565)
+    m, M = 9, n // 8
+    mu = (M - m + 1) / float(1 << m)
+    sig = np.sqrt(M * (1.0 / (1 << m) - (2.0 * m - 1.0) / (1 << 2 * m)))
+    chi = (((w.reshape(B, -1, 8).astype(np.float64) - mu) / sig) ** 2).sum(axis=2)
+    assert rel_err(fs[:, lay.fs_off[8]:lay.fs_off[8] + lay.ntemplates], chi).max() <= 1e-12
+
+
 def test_device_lcg_is_the_reference_generator(sts, oracle):
     with sts.Engine(max_streams=8) as eng:
         eng.generate_lcg(0, 8)
