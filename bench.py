@@ -18,6 +18,12 @@ skip-ahead so that rank r owns streams [r*1024, (r+1)*1024) - the reference's `-
   cpu_baseline  the unmodified reference binary (oracle/_ref/sts, built from /root/reference with the
           fftw3 shim) on all host cores, on a bounded sample of the same workload (rank 0, N = 1).
 
+  gather_check  (N > 1) rank 0 compares the gathered p-values of the last step, rank by rank in `-j` order, with what
+          it computes itself for those streams (bit-identical) and with the CPU oracle on a few sampled streams.
+  strong  BASELINE config 3 next to the weak-scaling headline: 16384 x 2^20-bit streams IN TOTAL sharded over the
+          N GPUs by the `-j` rule, p-values gathered to rank 0 (strong scaling: fixed total work).
+  roofline_all  every kernel group against its own roofline class.
+
 `--impl reference` times that reference binary alone (all host cores, bounded sample per step).
 The product path never touches oracle/: it is only executed here as the reported baseline.
 """
@@ -35,8 +41,22 @@ sys.path.insert(0, ROOT)
 
 N_BITS = 1 << 20
 STREAMS_PER_GPU = 1024
+REF_STREAMS_PER_CORE = 8
+FFT_NOTE = ("libfftw3 is not installed in this image: the reference binary is linked against the plain FP64 FFT of "
+            "oracle/fft_f64.c through a 5-symbol fftw3.h shim, so its DFT leg (about 2 % of its time) is slower than with FFTW")
+CONFIG3_TOTAL = 16384
 METRIC = "Gbit/s tested, all 15 tests on 2^20-bit streams"
 WORKLOAD = "1024x2^20-bit LCG streams per GPU, all 15 tests, default parameters (BASELINE config 2)"
+
+
+def csrc_sha256():
+    """hash of the engine's CUDA sources: ncu figures under profiles/ are only quoted for the build they were taken on"""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "sts_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "sts_b200", "csrc", "*.cuh"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
 
 
 def peaks():
@@ -167,7 +187,7 @@ def run_reference_arm(args, rank, world, dist):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = max(cores, 16)					# >= one stream per core, bounded
+    sample = REF_STREAMS_PER_CORE * cores			# several streams per thread: the wall time is not one slow thread's
     tmp = tempfile.mkdtemp(prefix="stsbench_")
     times = []
     kind = "reference"
@@ -183,8 +203,8 @@ def run_reference_arm(args, rank, world, dist):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "%d streams per step" % sample},
         "cpu_baseline": {"value": gbit, "unit": "Gbit/s", "cores": cores, "kind": kind,
-                         "sample": "%d x 2^20-bit LCG streams per step, sts -i %d -F r -T %d (file read included)"
-                                   % (sample, sample, cores)},
+                         "sample": "%d x 2^20-bit LCG streams per step, sts -i %d -F r -T %d (file read included); %s"
+                                   % (sample, sample, cores, FFT_NOTE)},
         "e2e": {"value": gbit, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,7 +227,7 @@ def main():
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         # bounded: a handful of multi-second runs, independent of the GPU arm's K/W
-        args.steps_ref = max(1, min(args.steps, 5))
+        args.steps_ref = max(1, min(args.steps, 3))
         args.warmup_ref = 1 if args.warmup > 0 else 0
         return run_reference_arm(args, rank, world, dist)
 
@@ -225,6 +245,9 @@ def main():
         uid = [sts_b200.Engine.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], rank, world)
+        # gather mode: the exchange of every batch's p-values to rank 0 is queued behind its tail kernels and
+        # overlaps the next batches; stsgpu_wait returns with the gathered array on rank 0's host
+        eng.gather_begin(0)
 
     # synthetic input: rank r owns LCG streams [r*B, (r+1)*B)  (the reference's -j partition),
     # generated into every batch slot so that the resident runs start with the input in HBM
@@ -243,12 +266,14 @@ def main():
     BINS = 32
     eng.assess_begin(BINS)
 
+    last_gather = [None]
+
     def finish_one(sink=None):
         eng.wait()
         if sink is not None:
             sink()
         if world > 1:
-            eng.gather_pvals(0, world)
+            last_gather[0] = eng.gather_pvals(0, world, copy=False)	# rank 0: all ranks' records of this step (pinned view)
 
     def run_steps(count, submit, sink=None, inflight=None):
         """exactly `count` batches submitted and completed, at most `inflight` (default DEPTH) in flight"""
@@ -310,6 +335,9 @@ def main():
     t1 = time.perf_counter()
     sec_e2e = max_over_ranks(dist, t1 - t0)
     clocks = sampler.stop() if rank == 0 else None
+    gathered_last = last_gather[0].copy() if (world > 1 and rank == 0) else None
+    if world > 1:
+        eng.gather_begin(-1)					# what follows is local to every rank
     e2e = world * B * N_BITS * K / sec_e2e / 1e9
     h2d = B * N_BITS // 8
     d2h = B * (lay.npv * 8 + lay.nst * 8 + lay.nw * 4)
@@ -326,6 +354,53 @@ def main():
                   "streams_assessed": int(verdict["sample"][lay.pv_off[1]]),
                   "columns_passing_uniformity_and_proportion": int((verdict["flags"] == 3).sum())}
 
+    eng.assess_begin(BINS)					# the steps below tally again, like the timed ones
+
+    # ---- gather_check (N > 1): the gathered records of the last timed step, rank by rank in -j order ----
+    gather_check = None
+    if world > 1:
+        if rank == 0:
+            same, worst = 0, 0.0
+            assert gathered_last.shape == (world * B, lay.npv), gathered_last.shape
+            for r in range(world):				# rank r tested streams [r*B, (r+1)*B): recompute them here
+                eng.generate_lcg(r * B, B)
+                eng.submit_resident(B, r * B)
+                eng.wait()
+                pv_r = eng.results(copy=False)[0]
+                same += int((gathered_last[r * B:(r + 1) * B] == pv_r).all())
+            # the CPU oracle as the checker (outside every timed region): one stream of every rank's block
+            from oracle import oracle as O
+            idx = [r * B + (37 * r + 11) % B for r in range(world)]
+            raw = np.concatenate([O.lcg_bytes(i, 1) for i in idx])
+            opv = O.run(O.make_params(), raw, len(idx), nthreads=os.cpu_count() or 1)[0]
+            got = gathered_last[idx]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rel = np.abs(got - opv) / np.abs(opv)
+            rel[got == opv] = 0.0
+            c3 = slice(lay.pv_off[3], lay.pv_off[3] + 2)
+            rel[:, c3][np.abs(got[:, c3] - opv[:, c3]) <= 1e-13] = 0.0	# cusum: 1 - sum + sum (tests/test_gpu_parity.py)
+            worst = float(rel.max())
+            gather_check = {"ranks": world, "streams": world * B, "blocks_identical_to_rank0_recompute": same,
+                            "oracle_streams": idx, "oracle_max_rel_err": worst,
+                            "ok": bool(same == world and worst <= 1e-9)}
+        barrier(dist)
+
+    # ---- strong scaling: BASELINE config 3, 16384 streams in total over the N GPUs, gathered to rank 0 ----
+    strong = None
+    if (CONFIG3_TOTAL // world) % B == 0:
+        from sts_b200.sharding import run_sharded
+        run_sharded(eng, world * B * 2, rank, world, B, collect=False)		# warm-up: two batches per rank
+        marks = []
+        barrier(dist)
+        run_sharded(eng, CONFIG3_TOTAL, rank, world, B, collect=False, timer=lambda: marks.append(time.perf_counter()))
+        barrier(dist)
+        sec3 = max_over_ranks(dist, marks[1] - marks[0])
+        strong = {"workload": "%d x 2^20-bit LCG streams in total (2 GiB), sharded over %d GPU(s) by the -j rule, all 15 tests, "
+                              "p-values gathered to rank 0 (BASELINE config 3)" % (CONFIG3_TOTAL, world),
+                  "scaling": "strong", "total_streams": CONFIG3_TOTAL, "n_gpus": world, "seconds": sec3,
+                  "value": CONFIG3_TOTAL * N_BITS / sec3 / 1e9, "unit": "Gbit/s",
+                  "input": "generated on the device batch by batch (generator included in the time)"}
+
     # ---- per-group durations with every group alone on the GPU (CUDA events, serialised pass) ----
     ktimes = {}
     eng.set_profiling(1)
@@ -341,18 +416,27 @@ def main():
     kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
     top = max(kavg, key=kavg.get)
     hbm_peak, peak_src = peaks()
-    if top == "dft":
-        alg_bytes = B * (2 * (N_BITS // 2) * 16 + N_BITS // 8)	# FP64 spectrum written + read, + packed input
-    else:
-        alg_bytes = B * (N_BITS // 8)
+    stream_bytes = N_BITS // 8
+    # algorithmic bytes per stream of every HBM-class group: the packed stream once per kernel;
+    # the DFT adds its FP64 spectrum written and read once; Universal reads only (Q + K) L bits
+    hbm_bytes = {"dft": 2 * (N_BITS // 2) * 16 + stream_bytes,
+                 "scan(freq,cusum,runs,excursions)": stream_bytes,
+                 "blocks(blockfreq,longestrun,overlapping)": 3 * stream_bytes,
+                 "universal": 113120}
+    alg_bytes = B * hbm_bytes.get(top, stream_bytes)
     achieved = alg_bytes / (kavg[top] * 1e-3) / 1e9
-    traffic = None
-    try:	# DRAM bytes of the same launches from the committed ncu capture (profiles/), scaled to B streams
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if top in tj["dram_bytes_per_group"] and tj["bits"] == N_BITS:
-            traffic = tj["dram_bytes_per_group"][top] * B / tj["streams"]
+    # what ncu measured (DRAM bytes, pipe utilisation per kernel) is only quoted while the kernels are the ones that
+    # were profiled: profiles/r2_ncu_summary.json records a hash of sts_b200/csrc at capture time
+    ncu = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
+        if tj.get("source_sha256") == csrc_sha256() and tj.get("bits") == N_BITS:
+            ncu = tj
     except Exception:
         pass
+    traffic = None
+    if ncu and top in ncu.get("dram_bytes_per_group", {}):
+        traffic = ncu["dram_bytes_per_group"][top] * B / ncu["streams"]
     roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kavg[top], "algorithmic_bytes_per_launch_group": alg_bytes,
@@ -361,17 +445,34 @@ def main():
                 "note": "kernel_ms / all_kernel_groups_ms: CUDA events around each kernel group with the groups "
                         "serialised (3 steps right after the timed region, same inputs); in_region_ms: the same "
                         "events inside the timed region, where several batches and five streams per batch overlap; "
-                        "see profiles/ for ncu"}
+                        "traffic: DRAM bytes from the ncu capture under profiles/, null when the kernels changed since"}
+    roofline_all = []
+    for name, ms in sorted(kavg.items(), key=lambda kv: -kv[1]):
+        e = {"kernel": name, "ms": round(ms, 4)}
+        if name in hbm_bytes:
+            a = B * hbm_bytes[name] / (ms * 1e-3) / 1e9
+            e.update({"bound": "hbm", "achieved": round(a, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(a / hbm_peak, 4)})
+        elif name.startswith("tails"):
+            e.update({"bound": "latency (igamc / erfc dependency chains, 1.5 KB of records per stream)", "achieved": None,
+                      "peak": None, "unit": None, "frac": None})
+        else:
+            # integer ALU (LinearComplexity, Rank) or shared-memory atomics (pattern histograms, templates): the
+            # utilisation of the limiting pipe as ncu measured it, quoted only for the profiled build
+            pipe = (ncu or {}).get("pipe_util_pct", {}).get(name)
+            e.update({"bound": "int-pipe" if name in ("linear_complexity", "rank") else "smem-atomic (LSU) pipe",
+                      "achieved": pipe, "peak": 100.0 if pipe is not None else None, "unit": "% of pipe (ncu)" if pipe is not None else None,
+                      "frac": round(pipe / 100.0, 4) if pipe is not None else None})
+        roofline_all.append(e)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(cores, 16)
+        sample = 4 * cores
         tmp = tempfile.mkdtemp(prefix="stsbench_")
         dt, kind = time_reference(sample, cores, tmp)
         cpu = {"value": sample * N_BITS / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
-               "sample": "%d x 2^20-bit LCG streams, `sts -i %d -F r -T %d` wall time %.1f s (file read included)"
-                         % (sample, sample, cores, dt)}
+               "sample": "%d x 2^20-bit LCG streams, `sts -i %d -F r -T %d` wall time %.1f s (file read included); %s"
+                         % (sample, sample, cores, dt, FFT_NOTE)}
 
     if rank == 0:
         line = {
@@ -381,13 +482,17 @@ def main():
             "config": {"workload": WORKLOAD, "streams_per_gpu_per_step": B, "bits_per_stream": N_BITS,
                        "l2": "input per step (128 MiB) exceeds L2; the FFT intermediate (8 GiB per step) flushes it",
                        "pipeline": "%d batch slots per GPU: 2 in flight for resident input, %d for host input (the upload of one overlaps the kernels of the others)" % (DEPTH, DEPTH),
-                       "sharding": "rank r tests streams [r*B,(r+1)*B), p-values gathered to rank 0 over NCCL"},
+                       "sharding": "rank r tests streams [r*B,(r+1)*B), p-values gathered to rank 0 over NCCL in gather mode "
+                                   "(the exchange of a batch is queued behind its kernels and overlaps the next batches)"},
             "device_ms_per_step": dev_step_ms,
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": sec_e2e / K * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_all": roofline_all,
+            "gather_check": gather_check,
+            "strong": strong,
             "cpu_baseline": cpu,
             "assessment": assessment,
         }

@@ -291,7 +291,8 @@ int stsgpu_comm_init(stsgpu_ctx *ctx, const uint8_t id[STSGPU_UNIQUE_ID_BYTES], 
  * `root` (grouped ncclSend / ncclRecv queued behind the batch's tail kernels, then the copy to the root's pinned
  * memory), so the exchange overlaps the kernels of the next batches and stsgpu_wait returns with the gathered array
  * already on the root's host - no separate blocking call per batch.  All ranks must submit the same sequence of
- * batches; "-F a" batches are refused in this mode.  Needs an idle engine and stsgpu_comm_init.
+ * batches; "-F a" batches are refused in this mode.  Needs an idle engine and stsgpu_comm_init.  root = -1 leaves
+ * gather mode again (batches submitted afterwards are local).
  */
 int stsgpu_gather_begin(stsgpu_ctx *ctx, int root);
 /*

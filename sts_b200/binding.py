@@ -300,15 +300,17 @@ class Engine:
         """gather mode: every batch submitted from now on ends with the exchange of its p-value records to `root`"""
         self._ck(self.lib.stsgpu_gather_begin(self.h, root), "gather_begin")
 
-    def gather_pvals(self, root=0, nranks=1):
+    def gather_pvals(self, root=0, nranks=1, copy=True):
+        """p-values of the last completed batch of every rank, rank-major, on `root` (None elsewhere); copy=False
+        returns a view of the engine's pinned buffer, valid until that batch slot completes again"""
         out = C.c_void_p()
         self._ck(self.lib.stsgpu_gather_pvals(self.h, root, C.byref(out)), "gather_pvals")
         if not out.value:
             return None
         ns = C.c_int64()
         self.lib.stsgpu_results(self.h, C.byref(ns), None, None, None, None)
-        return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)),
-                                     shape=(nranks * ns.value, self.layout.npv)).copy()
+        a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(nranks * ns.value, self.layout.npv))
+        return a.copy() if copy else a
 
     def comm_barrier(self):
         self._ck(self.lib.stsgpu_comm_barrier(self.h), "comm_barrier")

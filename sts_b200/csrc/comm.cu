@@ -222,6 +222,10 @@ extern "C" int stsgpu_gather_begin(stsgpu_ctx *ctx, int root)
 		snprintf(ctx->err, sizeof(ctx->err), "stsgpu_gather_begin needs an idle engine");
 		return STSGPU_E_STATE;
 	}
+	if (root == -1) {		/* leave gather mode */
+		ctx->gather_root = -1;
+		return STSGPU_OK;
+	}
 	if (root < 0 || root >= ctx->nranks || (ctx->nranks > 1 && ctx->nccl_comm == NULL))
 		return STSGPU_E_STATE;
 	if (cudaSetDevice(ctx->device) != cudaSuccess)

@@ -148,7 +148,9 @@ cudaError_t launch_blocks(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_rank(const DevParams &P, const LaunchCtx &L);
 cudaError_t launch_nonoverlapping(const DevParams &P, const LaunchCtx &L, const uint32_t *d_templates);
 cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist, uint32_t *d_flags);
-cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const unsigned long long *d_log2_table);
+cudaError_t launch_universal(const DevParams &P, const LaunchCtx &L, const unsigned long long *d_log2_table, uint32_t *d_dist,
+			     int64_t *launches);
+size_t universal_scratch_bytes_per_stream(const DevParams &P);
 cudaError_t launch_ascii_pack(const DevParams &P, const unsigned char *d_text, long long text_len, uint32_t *d_in,
 			      unsigned long long *d_status, int64_t nstreams, cudaStream_t stream);
 cudaError_t launch_lc(const DevParams &P, const LaunchCtx &L, const uint8_t *d_class_lut);

@@ -500,6 +500,11 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			CKC(pinned_alloc_near((void **) &S.h_fs, (size_t) B * lay.nfs * sizeof(double), ctx->device), "cudaMallocHost(fstats)");
 		}
 		CKC(cudaMalloc((void **) &S.d_hist_flags, (size_t) B * sizeof(uint32_t)), "cudaMalloc(hist flags)");
+		{	/* Universal split over several warps per stream: 4 bytes of scratch per test block, when that stays below 2 GiB */
+			const size_t per = universal_scratch_bytes_per_stream(P);
+			if (per != 0 && per * (size_t) B <= ((size_t) 2 << 30))
+				CKC(cudaMalloc((void **) &S.d_uni_dist, per * (size_t) B), "cudaMalloc(universal distances)");
+		}
 		if (want_apen)
 			CKC(cudaMalloc((void **) &S.d_apen_hist, (size_t) B * ((size_t) 3 << p->apen_m) * sizeof(uint32_t)),
 			    "cudaMalloc(apen histograms)");
@@ -689,7 +694,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		cudaFree(S.d_in); cudaFree(S.d_pv); cudaFree(S.d_st); cudaFree(S.d_w);
 		cudaFreeHost(S.h_pv); cudaFreeHost(S.h_st); cudaFreeHost(S.h_w);
 		cudaFree(S.d_fs); cudaFreeHost(S.h_fs);
-		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags);
+		cudaFree(S.d_apen_hist); cudaFree(S.d_dft_work); cudaFree(S.d_hist_flags); cudaFree(S.d_uni_dist);
 		cudaFree(S.d_text); cudaFree(S.d_ascii); cudaFreeHost(S.h_ascii);
 		if (S.s_light) cudaStreamDestroy(S.s_light);
 		if (S.s_heavy) cudaStreamDestroy(S.s_heavy);
@@ -802,12 +807,10 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 		case G_RANK: e = launch_rank(P, L); launched = 1; break;
 		case G_NONOV: e = launch_nonoverlapping(P, L, ctx->d_templates); launched = 1; break;
 		case G_PATTERN: e = launch_pattern(P, L, S.d_apen_hist, S.d_hist_flags); launched = 2; break;
-		case G_UNIVERSAL: e = launch_universal(P, L, ctx->d_log2tab); launched = 1; break;
+		case G_UNIVERSAL: e = launch_universal(P, L, ctx->d_log2tab, S.d_uni_dist, &launched); break;
 		case G_LC: e = launch_lc(P, L, ctx->d_class_lut); launched = 1; break;
 		case G_DFT:
-			e = launch_dft(P, L, ctx->dft, S.d_dft_work, ctx->dft_chunk);
-			launched = (P.enabled & (1u << STSGPU_TEST_DFT))
-				? (ctx->dft.fast == 3 ? dft_any_launches_per_chunk(ctx->dft) : 2) * ((nstreams + ctx->dft_chunk - 1) / ctx->dft_chunk) : 0;
+			e = launch_dft(P, L, ctx->dft, S.d_dft_work, ctx->dft_chunk, &launched);
 			break;
 		}
 		if (e != cudaSuccess) {

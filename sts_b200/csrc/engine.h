@@ -30,6 +30,7 @@ struct Slot {
 	double *d_hdr = nullptr, *h_hdr = nullptr, *d_hdr_all = nullptr, *h_hdr_all = nullptr;
 	bool gathered = false;
 	uint32_t *d_apen_hist = nullptr;
+	uint32_t *d_uni_dist = nullptr;		/* Universal: the distance of every test block (k_universal.cu, split kernels) */
 	uint32_t *d_hist_flags = nullptr;	/* streams the packed 16-bit histogram could not count exactly */
 	double2 *d_dft_work = nullptr;
 	/* "-F a" batches (k_ascii.cu): text staging, {first incomplete stream, first bad character} */
@@ -105,7 +106,7 @@ int stsgpu_comm_enqueue_gather(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, cudaS
 
 cudaError_t launch_tails(const DevParams &P, const TailConsts &K, const LaunchCtx &L, const uint32_t *d_apen_hist,
 			 cudaStream_t s_cusum, cudaStream_t s_apen);
-cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
+cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams, int64_t *launches);
 cudaError_t launch_assess_tally(const DevParams &P, const LaunchCtx &L, int64_t bins, double alpha, unsigned long long *d_tally,
 				const unsigned long long *d_limit);
 cudaError_t launch_assess_add(const DevParams &P, int pv_off, int pv_cnt, const double *d_vals, int64_t count, int64_t first_index,

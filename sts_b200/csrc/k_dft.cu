@@ -332,10 +332,14 @@ bool dft_make_plan(long long n, DftPlan *D)
 	return true;
 }
 
-cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams)
+cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams,
+		       int64_t *launches)
 {
+	*launches = 0;
 	if (!(P.enabled & (1u << STSGPU_TEST_DFT)))
 		return cudaSuccess;
+	const int64_t chunks = (L.nstreams + work_streams - 1) / work_streams;
+	*launches = (D.fast == 3 ? dft_any_launches_per_chunk(D) : 2) * chunks;
 	if (D.fast == 1)
 		return launch_dft_fast(P, L, D, d_work, work_streams);
 	if (D.fast == 2)

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "dft.h"
 #include "dft_math.cuh"
+#include "dft16.cuh"
 
 #ifndef DFT_MINCTA
 #define DFT_MINCTA 2
@@ -50,8 +51,6 @@
 #ifndef DFT_NO_TW_POWERS
 #define DFT_TW_POWERS 1	/* fewer table lookups: r = 1, 2, 4, 8 loaded, the other twiddle powers by products */
 #endif
-#define QN1 256
-#define QN2 2048
 #ifndef QCW
 #define QCW 8				/* columns per CTA in the column pass (16 threads per column): 128-thread CTAs, four per SM.  Measured DFT group / pipelined batch per 1024 streams: QCW 16 4.45 / 9.84 ms, 8 4.25 / 9.35 ms, 4 4.73 / 9.85 ms */
 #endif
@@ -59,59 +58,6 @@
 #define QCOLS_MINCTA (DFT_MINCTA * 16 / QCW)
 #endif
 #define QCOLS_BOUNDS __launch_bounds__(16 * QCW, QCOLS_MINCTA)
-#define QROW (QN2 + QN2 / 16)		/* padded row: one spare element per 16 */
-
-__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
-
-/* 16-point DFT in registers, natural order in and out: j = j0 + 4 j1, k = k1 + 4 k0 */
-__device__ __forceinline__ void bfly16(double2 *v)
-{
-	const double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, r2 = 0.70710678118654752440;
-	double2 a[16];
-#pragma unroll
-	for (int j0 = 0; j0 < 4; j0++) {
-		double2 t[4] = { v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12] };
-		bfly<4>(t);
-#pragma unroll
-		for (int k1 = 0; k1 < 4; k1++)
-			a[j0 * 4 + k1] = t[k1];
-	}
-	/* times W_16^(j0 k1) */
-	a[5] = cmul(a[5], make_double2(c8, -s8));			/* W^1 */
-	a[6] = make_double2(r2 * (a[6].x + a[6].y), r2 * (a[6].y - a[6].x));	/* W^2 */
-	a[7] = cmul(a[7], make_double2(s8, -c8));			/* W^3 */
-	a[9] = make_double2(r2 * (a[9].x + a[9].y), r2 * (a[9].y - a[9].x));	/* W^2 */
-	a[10] = cmi(a[10]);						/* W^4 = -i */
-	a[11] = make_double2(r2 * (a[11].y - a[11].x), -r2 * (a[11].x + a[11].y));	/* W^6 */
-	a[13] = cmul(a[13], make_double2(s8, -c8));			/* W^3 */
-	a[14] = make_double2(r2 * (a[14].y - a[14].x), -r2 * (a[14].x + a[14].y));	/* W^6 */
-	a[15] = cmul(a[15], make_double2(-c8, s8));			/* W^9 */
-#pragma unroll
-	for (int k1 = 0; k1 < 4; k1++) {
-		double2 t[4] = { a[k1], a[4 + k1], a[8 + k1], a[12 + k1] };
-		bfly<4>(t);
-#pragma unroll
-		for (int k0 = 0; k0 < 4; k0++)
-			v[k1 + 4 * k0] = t[k0];
-	}
-}
-
-/* x times W_16^r = exp(-2 pi i r / 16), r = 0..7 (compile-time r after unrolling) */
-__device__ __forceinline__ double2 cmul_w16(double2 x, int r)
-{
-	const double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, r2 = 0.70710678118654752440;
-	switch (r) {
-	case 0: return x;
-	case 1: return cmul(x, make_double2(c8, -s8));
-	case 2: return make_double2(r2 * (x.x + x.y), r2 * (x.y - x.x));
-	case 3: return cmul(x, make_double2(s8, -c8));
-	case 4: return cmi(x);
-	case 5: return cmul(x, make_double2(-s8, -c8));
-	case 6: return make_double2(r2 * (x.y - x.x), -r2 * (x.x + x.y));
-	default: return cmul(x, make_double2(-c8, -s8));
-	}
-}
-
 /* ------------------------------------------------------------------------------------------ */
 __global__ void QCOLS_BOUNDS
 dft_cols16(DevParams P, DftPlan D, const uint32_t *__restrict__ in, double2 *__restrict__ Y, int64_t stream0)
@@ -301,8 +247,15 @@ dft_rows16(DevParams P, DftPlan D, const double2 *__restrict__ Y, long long *__r
 			  (unsigned long long) cnt_s);
 }
 
+cudaError_t launch_dft_rows_tma(const DevParams &P, const DftPlan &D, const double2 *d_work, long long *d_st, int64_t stream0, int64_t cs,
+				int num_sms, cudaStream_t stream);
+
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams)
 {
+	/* row pass: the persistent TMA-fed kernel of k_dft_rows_tma.cu, or (STSGPU_DFT_ROWS_TMA=0) dft_rows16 below */
+	static int rows_tma = -1;
+	if (rows_tma < 0)
+		rows_tma = getenv("STSGPU_DFT_ROWS_TMA") ? atoi(getenv("STSGPU_DFT_ROWS_TMA")) : 0;
 	const size_t smem1 = (size_t) QN1 * QCW * sizeof(double2);
 	const size_t smem2 = (size_t) 2 * QROW * sizeof(double2);
 	cudaError_t e;
@@ -329,8 +282,13 @@ cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPla
 		double2 *wk = d_work + (size_t) which * work_streams * ((size_t) QN1 * QN2);
 		dim3 g1((unsigned) cs, QN2 / QCW);
 		dft_cols16<<<g1, 16 * QCW, smem1, st>>>(P, D, L.d_in, wk, s0);
-		dim3 g2((unsigned) cs, QN1 / 2 + 1);
-		dft_rows16<<<g2, 256, smem2, st>>>(P, D, wk, L.d_st, s0);
+		if (rows_tma) {
+			e = launch_dft_rows_tma(P, D, wk, L.d_st, s0, cs, L.num_sms, st);
+			if (e != cudaSuccess) return e;
+		} else {
+			dim3 g2((unsigned) cs, QN1 / 2 + 1);
+			dft_rows16<<<g2, 256, smem2, st>>>(P, D, wk, L.d_st, s0);
+		}
 	}
 	if (two) {
 		e = cudaEventRecord(L.ev2_join, L.stream2);

@@ -15,6 +15,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -247,7 +248,60 @@ static inline double __dmul_rn(double a, double b) { volatile double r = a * b; 
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long) (((unsigned __int128) a * b) >> 64); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((uint64_t) a * b) >> 32); }
+#define __log2f(x) log2f(x)	/* glibc declares a function of this name */
 template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+template <class T> static inline void __stcg(T *p, T v) { *p = v; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+/*
+ * mbarrier + bulk copy (sts_b200/csrc/tma.cuh).  The 64-bit barrier word holds {phase:1, arrivals pending:15,
+ * arrivals per phase:16, transaction bytes pending:32 (signed)}; the threads of a CTA are cooperative fibers on one
+ * OS thread, so plain read-modify-write is enough.  A bulk copy is performed at issue time.
+ */
+namespace emu { void fiber_yield(); void note_progress(); }
+static inline void emu_mbar_settle(uint64_t *bar)
+{
+	uint64_t v = *bar;
+	const uint32_t pending = (uint32_t) ((v >> 1) & 0x7fffu), per_phase = (uint32_t) ((v >> 16) & 0xffffu);
+	const int32_t tx = (int32_t) (v >> 32);
+	if (pending == 0 && tx == 0)		/* phase complete: flip, re-arm */
+		*bar = ((v & 1u) ^ 1u) | ((uint64_t) per_phase << 1) | ((uint64_t) per_phase << 16);
+}
+static inline void mbar_init(uint64_t *bar, uint32_t arrivals) { *bar = ((uint64_t) arrivals << 1) | ((uint64_t) arrivals << 16); }
+static inline void mbar_fence_init() {}
+static inline void emu_mbar_update(uint64_t *bar, int arrive, int64_t tx_delta)
+{
+	uint64_t v = *bar;
+	uint32_t pending = (uint32_t) ((v >> 1) & 0x7fffu);
+	int32_t tx = (int32_t) (v >> 32);
+	if (arrive) {
+		if (pending == 0) { fprintf(stderr, "cuda_emu: mbarrier arrival beyond its count\n"); abort(); }
+		pending--;
+	}
+	tx += (int32_t) tx_delta;
+	*bar = (v & 0xffff0001ull) | ((uint64_t) pending << 1) | ((uint64_t) (uint32_t) tx << 32);
+	emu_mbar_settle(bar);
+	emu::note_progress();
+}
+static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { emu_mbar_update(bar, 1, (int64_t) bytes); }
+static inline void mbar_arrive(uint64_t *bar) { emu_mbar_update(bar, 1, 0); }
+static inline void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	while ((uint32_t) (*(volatile uint64_t *) bar & 1u) == parity)	/* still in the phase with this parity */
+		emu::fiber_yield();
+}
+static inline void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+	if ((bytes & 15u) || ((uintptr_t) smem_dst & 15u) || ((uintptr_t) gmem_src & 15u)) {
+		fprintf(stderr, "cuda_emu: bulk copy needs 16-byte aligned addresses and size\n");
+		abort();
+	}
+	memcpy(smem_dst, gmem_src, bytes);
+	emu_mbar_update(bar, 0, -(int64_t) bytes);
+}
+static inline void fence_proxy_async() {}
+void emu_nanosleep(unsigned ns);	/* lets the OS thread's other work (other CTAs on other OS threads) make progress */
+static inline void __nanosleep(unsigned ns) { emu_nanosleep(ns); }
 template <class T> static inline size_t __cvta_generic_to_shared(const T *p) { return (size_t) p; }
 
 /* CUDA's global min / max accept mixed integer types */

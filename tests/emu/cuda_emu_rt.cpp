@@ -2,6 +2,7 @@
  * cuda_emu_rt.cpp - TEST INFRASTRUCTURE (see cuda_emu.h): the fiber scheduler that steps the threads of a CTA
  * through barriers and warp collectives, and a synchronous stand-in for the few CUDA runtime calls the engine makes.
  */
+#include <sched.h>
 #include "cuda_emu.h"
 #include <stdio.h>
 #include <time.h>
@@ -87,6 +88,11 @@ static Block *new_block()
 }
 
 void *dyn_smem() { return blk->smem; }
+
+/* a thread that polls (an mbarrier another thread of the CTA will complete) lets the other fibers run; polling is not
+ * progress (the deadlock check must still fire when every thread polls for ever), an mbarrier update is */
+void fiber_yield() { emu_switch(&curf->sp, blk->sched_sp); }
+void note_progress() { blk->ticks++; }
 
 static inline void yield() { emu_switch(&curf->sp, blk->sched_sp); }
 
@@ -444,3 +450,9 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
+
+void emu_nanosleep(unsigned ns)
+{
+	(void) ns;
+	sched_yield();
+}
