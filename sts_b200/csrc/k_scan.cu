@@ -3,7 +3,7 @@
  * CumulativeSums (cusum.c:221-236), Runs (runs.c:213-240), RandomExcursions
  * (randomExcursions.c:318-464) and RandomExcursionsVariant (randomExcursionsVariant.c:248-306).
  *
- * One CTA per bitstream, the stream taken in chunks of 1024 rows of 1024 bits (lane l of a warp holds
+ * One CTA per bitstream, the stream taken in chunks of SCAN_ROWS (256) rows of 1024 bits (lane l of a warp holds
  * word l of a row, so global loads are 128-byte coalesced):
  *   pass 1: popcount of every row -> block-wide exclusive scan = the random walk value S at the
  *           start of every row (and the last bit of every row for the run count);
@@ -19,13 +19,14 @@
  *           256 threads -> 8 warps -> 1 thread.  Visit counts saturate at 5 in 4-bit fields (only
  *           min(count, 5) is used, randomExcursions.c:441-451).
  *
- * Algorithmic bytes: n/8 per stream (the second pass re-reads the stream from L1/L2).
+ * Algorithmic bytes: n/8 per stream (the second pass re-reads a 32 KiB chunk right after the first: L1/L2 hits).
  */
 #include "common.cuh"
 
 #define SCAN_WARPS 8
 #define SCAN_THREADS (SCAN_WARPS * 32)
-#define SCAN_ROWS 1024			/* rows per chunk */
+#define SCAN_ROWS 256			/* rows per chunk: 32 KiB of stream, still in L2 (and mostly in L1) when pass 2 reads it again */
+#define SCAN_RPT (SCAN_ROWS / SCAN_THREADS)	/* rows per thread in the block scans */
 
 /* saturating (at 5) add of two words of eight 4-bit counters */
 __device__ __forceinline__ uint32_t nib_satadd5(uint32_t a, uint32_t b)
@@ -89,6 +90,7 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 	__shared__ unsigned int v_s[6 * 8];
 	__shared__ unsigned int xi_s[18][SCAN_THREADS];
 	__shared__ int red_max[SCAN_WARPS], red_min[SCAN_WARPS], red_trans[SCAN_WARPS];
+	__shared__ int chunk_hot;				/* some row of this chunk came within the excursion states */
 
 	const int64_t s = blockIdx.x;
 	if (s >= nstreams)
@@ -125,17 +127,23 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 	for (int64_t c0 = 0; c0 < nrows; c0 += SCAN_ROWS) {
 		const int crow = (int) min((int64_t) SCAN_ROWS, nrows - c0);
 		__syncthreads();				/* previous chunk's shared arrays are consumed */
-		/* ---- pass 1: ones and last bit of every row ---- */
-		for (int r = warp; r < crow; r += SCAN_WARPS) {
-			const int64_t idx = (c0 + r) * 32 + lane;
-			const uint32_t wd = (idx < nwords) ? ldw(w, idx) : 0u;
-			const int ones = warp_sum(__popc(wd));
-			/* last valid bit of the row: stream bit min(n, 1024 (row + 1)) - 1 */
-			const int64_t lastbit = min(n, (c0 + r + 1) * 1024) - 1;
-			const uint32_t lw = __shfl_sync(0xffffffffu, wd, (int) ((lastbit >> 5) & 31));
-			if (lane == 0) {
-				row_S[r] = ones;
-				row_last[r] = (uint8_t) ((lw >> (31 - (int) (lastbit & 31))) & 1u);
+		/*
+		 * ---- pass 1: ones and last bit of every row.  Sixteen bytes per thread, a row = 8 consecutive lanes; the words
+		 * behind the stream's end are zero padding up to the pitch, so whole rows are read.  The last bit of a row is only
+		 * ever used by the row that follows it (a ragged last row has none).
+		 */
+		{
+			const uint4 *__restrict__ w4 = (const uint4 *) (w + c0 * 32);
+			for (int q = tid; q < ((crow * 8 + 31) & ~31); q += SCAN_THREADS) {	/* whole warps: the shuffles below are full-mask */
+				const uint4 v = (q < crow * 8) ? __ldg(w4 + q) : make_uint4(0u, 0u, 0u, 0u);
+				int ones = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+				ones += __shfl_xor_sync(0xffffffffu, ones, 1);
+				ones += __shfl_xor_sync(0xffffffffu, ones, 2);
+				ones += __shfl_xor_sync(0xffffffffu, ones, 4);
+				if ((lane & 7) == 0 && q < crow * 8)
+					row_S[q >> 3] = ones;
+				if ((lane & 7) == 7 && q < crow * 8)
+					row_last[q >> 3] = (uint8_t) (bswap32(v.w) & 1u);
 			}
 		}
 		for (int r = tid; r < SCAN_ROWS; r += SCAN_THREADS) {
@@ -143,13 +151,15 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 			row_pre[r] = 0;
 			row_suf[r] = 0;
 		}
+		if (tid == 0)
+			chunk_hot = 0;
 		__syncthreads();
-		/* ---- block scan: walk value at every row start (4 consecutive rows per thread) ---- */
+		/* ---- block scan: walk value at every row start (SCAN_RPT consecutive rows per thread) ---- */
 		{
-			int d[4], loc = 0;
+			int d[SCAN_RPT], loc = 0;
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int r = 4 * tid + j;
+			for (int j = 0; j < SCAN_RPT; j++) {
+				const int r = SCAN_RPT * tid + j;
 				int v = 0;
 				if (r < crow) {
 					const int64_t b0 = min(n, (c0 + r) * 1024), b1 = min(n, (c0 + r + 1) * 1024);
@@ -167,8 +177,8 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 			for (int j = 0; j < warp; j++)
 				base += warp_tot[j];
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int r = 4 * tid + j;
+			for (int j = 0; j < SCAN_RPT; j++) {
+				const int r = SCAN_RPT * tid + j;
 				if (r < crow)
 					row_S[r] = base;
 				base += d[j];
@@ -191,7 +201,12 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 			const int Sb = row_S[r] + incl - d;
 
 			/* cusum: max / min prefix inside the word */
-			if (vb == 32) {
+			int wmx = 41, wmn = -41;			/* reach of the walk inside this word, relative to Sb */
+			/* the byte LUT only where it can matter: a new extreme for this lane, or a word near the excursion states */
+			const bool look = Sb + 32 > smax || Sb - 32 < smin || abs(Sb) <= 41;
+			if (vb == 32 && !look) {
+				/* nothing to record */
+			} else if (vb == 32) {
 				int run_ = 0, mx = -64, mn = 64;
 #pragma unroll
 				for (int k = 3; k >= 0; k--) {
@@ -202,6 +217,8 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 				}
 				smax = max(smax, Sb + mx);
 				smin = min(smin, Sb + mn);
+				wmx = mx;
+				wmn = mn;
 			} else if (vb > 0) {
 				int run_ = Sb;
 				for (int p = 0; p < vb; p++) {
@@ -221,9 +238,9 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 				m &= 0x7FFFFFFFu;
 			trans += __popc(x & m);
 
-			/* excursions: only words that can reach |S| <= 9 */
+			/* excursions: only words whose walk comes within the states -9 .. 9 (the prefix extremes are known from the cusum LUT) */
 			if (want_exc) {
-				const bool hot = vb > 0 && abs(Sb) <= 41;
+				const bool hot = vb > 0 && abs(Sb) <= 41 && Sb + wmn <= 9 && Sb + wmx >= -9;
 				if (__any_sync(0xffffffffu, hot)) {
 					Exc e;
 					e.nz = e.pre = e.suf = 0;
@@ -231,6 +248,15 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 						uint32_t cur = 0;
 						int Sx = Sb;
 						for (int p = 0; p < vb; p++) {
+							if ((p & 7) == 0 && p + 8 <= vb) {
+								/* a byte that stays outside -9 .. 9 only moves the walk */
+								const uint32_t be = lut[(wd >> (24 - p)) & 255u];
+								if (Sx + (int) ((be >> 16) & 255u) - 8 > 9 || Sx + (int) ((be >> 8) & 255u) - 8 < -9) {
+									Sx += (int) (be & 255u) - 8;
+									p += 7;
+									continue;
+								}
+							}
 							Sx += ((wd >> (31 - p)) & 1u) ? 1 : -1;
 							if (Sx == 0) {
 								if (e.nz == 0)
@@ -270,6 +296,7 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 						row_nz[r] = e.nz;
 						row_pre[r] = e.pre;
 						row_suf[r] = e.suf;
+						chunk_hot = 1;
 					}
 				}
 			}
@@ -278,13 +305,13 @@ scan_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict_
 		__syncthreads();
 		last0 = row_last[crow - 1];
 
-		/* ---- pass 3: merge the row summaries in order: 4 rows per thread, 32 threads per warp, 8 warps ---- */
-		if (want_exc) {
+		/* ---- pass 3: merge the row summaries in order: SCAN_RPT rows per thread, 32 threads per warp, 8 warps ---- */
+		if (want_exc && chunk_hot) {			/* the summary of a chunk without hot rows is the identity */
 			Exc e;
 			e.nz = e.pre = e.suf = 0;
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int r = 4 * tid + j;
+			for (int j = 0; j < SCAN_RPT; j++) {
+				const int r = SCAN_RPT * tid + j;
 				Exc b;
 				b.nz = row_nz[r];
 				b.pre = row_pre[r];
