@@ -212,6 +212,52 @@ def run_reference_arm(args, rank, world, dist):
     return 0
 
 
+def run_config4(sts_b200, device, streams=428, steps=4):
+    """BASELINE config 4 as a measured configuration: `streams` LCG streams of 10^7 bits (4 x the 107 streams that
+    1024 Mi-bit of generator output hold), -P 6=5000,2=10,4=16,5=16; BlockFrequency self-disables at this n
+    (blockFrequency.c:119), 323 p-values per stream.  Resident input, two batches in flight; per-group times from a
+    serialised pass afterwards."""
+    n = 10 ** 7
+    eng = sts_b200.Engine(device=device, max_streams=streams, n=n, linear_complexity_M=5000, non_overlapping_m=10,
+                          apen_m=16, serial_m=16, pipeline_depth=2)
+    try:
+        for d in range(2):
+            eng.generate_lcg(0, streams)
+            eng.submit_resident(streams, 0)
+        eng.wait()
+        eng.wait()
+        for i in range(2):                                   # warm-up
+            eng.submit_resident(streams, 0)
+            eng.wait()
+        t0 = time.perf_counter()
+        pending = 0
+        for i in range(steps):
+            eng.submit_resident(streams, 0)
+            pending += 1
+            if pending == 2:
+                eng.wait()
+                pending -= 1
+        while pending:
+            eng.wait()
+            pending -= 1
+        sec = (time.perf_counter() - t0) / steps
+        eng.set_profiling(1)
+        acc = {}
+        for i in range(3):
+            eng.submit_resident(streams, 0)
+            eng.wait()
+            if i >= 1:
+                for name, ms in eng.kernel_times():
+                    acc.setdefault(name, []).append(ms)
+        return {"workload": "%d x 10^7-bit LCG streams, -P 6=5000,2=10,4=16,5=16 (BASELINE config 4), 14 tests, %d p-values per stream"
+                            % (streams, eng.layout.npv),
+                "streams_per_step": streams, "bits_per_stream": n, "steps": steps, "ms_per_step": sec * 1e3,
+                "ms_per_107_streams": sec * 1e3 * 107.0 / streams, "value": streams * n / sec / 1e9, "unit": "Gbit/s",
+                "kernel_groups_ms_serialised": {k: round(sum(v) / len(v), 3) for k, v in acc.items()}}
+    finally:
+        eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -221,6 +267,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config-4 block")
     args = ap.parse_args()
 
     rank, world, local, dist = (0, 1, 0, None)
@@ -464,6 +511,12 @@ def main():
                       "frac": round(pipe / 100.0, 4) if pipe is not None else None})
         roofline_all.append(e)
 
+    # ---- BASELINE config 4 (n = 10^7, LinearComplexity M = 5000, template m = 10, Serial/ApEn m = 16) on this GPU ----
+    config4 = None
+    if rank == 0 and not args.no_config4:
+        config4 = run_config4(sts_b200, local)
+    barrier(dist)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -493,6 +546,7 @@ def main():
             "roofline_all": roofline_all,
             "gather_check": gather_check,
             "strong": strong,
+            "config4": config4,
             "cpu_baseline": cpu,
             "assessment": assessment,
         }
