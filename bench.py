@@ -418,7 +418,11 @@ def main():
             # the CPU oracle as the checker (outside every timed region): one stream of every rank's block
             from oracle import oracle as O
             idx = [r * B + (37 * r + 11) % B for r in range(world)]
-            raw = np.concatenate([O.lcg_bytes(i, 1) for i in idx])
+            raws = []
+            for i in idx:			# the device generator (pinned to tools/generators by the tests) has skip-ahead, the CPU one has not
+                eng.generate_lcg(i, 1)
+                raws.append(eng.download_input(1))
+            raw = np.concatenate(raws)
             opv = O.run(O.make_params(), raw, len(idx), nthreads=os.cpu_count() or 1)[0]
             got = gathered_last[idx]
             with np.errstate(divide="ignore", invalid="ignore"):

@@ -63,15 +63,21 @@ if rank == 0:
             one.wait()
             single[b * B:(b + 1) * B] = one.results(copy=False)[0]
         lay = one.layout
+        # the sampled streams for the oracle come from the device generator (byte-identical to tools/generators 1, see
+        # test_device_lcg_is_the_reference_generator): the CPU generator has no skip-ahead and would walk 10^10 steps
+        k = max(world, args.oracle_streams)
+        idx = sorted(set(int(x) for x in np.linspace(0, world * per - 1, k)) |
+                     set(shard_range(args.total, r, world)[0] for r in range(world)) |		# first and last iteration of every job
+                     set(shard_range(args.total, r, world)[1] - 1 for r in range(world)))
+        raws = []
+        for i in idx:
+            one.generate_lcg(i, 1)
+            raws.append(one.download_input(1))
+        raw = np.concatenate(raws)
     bad_rows = np.flatnonzero((allpv != single).any(axis=1))
     identical = bad_rows.size == 0
     # (2) the oracle on streams spread over all slices, in -j order
     from oracle import oracle as O
-    k = max(world, args.oracle_streams)
-    idx = sorted(set(int(x) for x in np.linspace(0, world * per - 1, k)) |
-                 set(shard_range(args.total, r, world)[0] for r in range(world)) |		# first and last iteration of every job
-                 set(shard_range(args.total, r, world)[1] - 1 for r in range(world)))
-    raw = np.concatenate([O.lcg_bytes(i, 1) for i in idx])
     opv = O.run(O.make_params(), raw, len(idx), nthreads=os.cpu_count() or 1)[0]
     got = allpv[idx]
     with np.errstate(divide="ignore", invalid="ignore"):
