@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include "utils/externs.h"
 #include "utils/utilities.h"
@@ -667,6 +668,14 @@ read_sequential(struct state *state, uint8_t *dst, long int streams, long int fi
 
 /* ------------------------------------------------------------------------------------------------------------ */
 
+static double
+now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
 static void
 engine_fatal(int code, const char *name, const char *what, int rc)
 {
@@ -811,12 +820,15 @@ invokeTestSuite(struct state *state)
 	bool eof = false, short_seen = false;
 	int w = 0, rc;
 	char tbuf[BUFSIZ + 1];	// time string buffer
+	double t_read = 0.0, t_wait = 0.0, t_keep = 0.0;
+	const double t_begin = now_s();
 
 	for (;;) {
 		while (stsgpu_pending(G.engine) < depth && !eof && submitted < total) {
 			const long int want = MIN(B, total - submitted);
 			long int have = want;
 			uint8_t *dst = buf[w % depth];
+			const double t_r0 = now_s();
 			if (text) {
 				/* iteration k = the first n digits at or after character base_seek + k n (the fseek of :1682) */
 				const long int off = state->base_seek + submitted * n;
@@ -855,13 +867,17 @@ invokeTestSuite(struct state *state)
 			want_of[w % depth] = have;
 			submitted += have;
 			w++;
+			t_read += now_s() - t_r0;
 		}
 		if (stsgpu_pending(G.engine) == 0)
 			break;
+		const double t_w0 = now_s();
 		rc = stsgpu_wait(G.engine);
 		if (rc != STSGPU_OK) {
 			engine_fatal(229, __func__, "the GPU engine failed on a batch", rc);
 		}
+		const double t_k0 = now_s();
+		t_wait += t_k0 - t_w0;
 		int64_t bn = 0, bf = 0;
 		stsgpu_results(G.engine, &bn, &bf, &G.pv, &G.st, &G.w);
 		stsgpu_results_stats(G.engine, &G.fs);
@@ -910,7 +926,11 @@ invokeTestSuite(struct state *state)
 			}
 		}
 		done += (long int) bn;
+		t_keep += now_s() - t_k0;
 	}
+	dbg(DBG_LOW, "iterate phase on the GPU: %ld streams of %ld bits in %.3f s = %.2f Gbit/s (read + submit %.3f s, waiting for the "
+	    "GPU %.3f s, iterate() record keeping %.3f s)", done, n, now_s() - t_begin, (double) done * (double) n / (now_s() - t_begin) / 1e9,
+	    t_read, t_wait, t_keep);
 	state->iterationsMissing = total - done;
 	if (done < total) {
 		/*

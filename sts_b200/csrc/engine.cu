@@ -510,7 +510,13 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			    "cudaMalloc(apen histograms)");
 		CKC(cudaStreamCreateWithPriority(&S.s_light, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_heavy, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
-		CKC(cudaStreamCreateWithPriority(&S.s_uni, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
+		{	/* Universal was one latency chain per stream (high priority: let it start early); split over eight warps per
+			 * stream it is a throughput kernel that fills every warp slot of an SM: low priority like the other big grids
+			 * (measured: no difference for the pipelined batch either way; STSGPU_UNI_PRIO=1 restores the old setting) */
+			const char *up = getenv("STSGPU_UNI_PRIO");
+			const int uni_prio = (up && atoi(up) > 0) ? prio_hi : prio_lo;
+			CKC(cudaStreamCreateWithPriority(&S.s_uni, cudaStreamNonBlocking, uni_prio), "cudaStreamCreate");
+		}
 		CKC(cudaStreamCreateWithPriority(&S.s_dft[0], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
 		CKC(cudaStreamCreateWithPriority(&S.s_dft[1], cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
 		CKC(cudaEventCreateWithFlags(&S.ev_join_uni, cudaEventDisableTiming), "cudaEventCreate");

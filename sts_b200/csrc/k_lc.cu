@@ -206,6 +206,12 @@ lc_kernel_win(DevParams P, const uint32_t *__restrict__ in, const uint8_t *__res
  * masks: a step is one AND-XOR, one rotate-shuffle and one funnel shift per live slot plus one redux.sync.
  * The slot range is re-derived every 256 steps and selects one of WPL (WPL + 1) / 2 unrolled bodies.
  * (The per-thread local-memory kernel below took 83 % of a BASELINE config 4 batch.)
+ *
+ * Tried in round 2 and measured slower (200 against 120 ms per 428 streams of config 4): one block per group of EIGHT
+ * lanes, four blocks per warp, 20 slots per lane.  More live slots per lane amortise the per-step overhead, but the
+ * four blocks of a warp take different paths, so every update becomes a mask operation that runs on every step
+ * (here the discrepancy is warp-uniform and half of the steps skip the update), and the rotate-shuffle per live slot
+ * - five to ten per step instead of one to three - saturates the shuffle path.
  */
 template <int WPL, int SLO, int SHI>
 __device__ __forceinline__ void lc_warp_steps(const uint32_t (&S)[WPL], uint32_t (&C)[WPL], uint32_t (&B)[WPL], int &L, int Na,

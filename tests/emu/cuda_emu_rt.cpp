@@ -45,10 +45,18 @@ static const size_t STACK_BYTES = 256 * 1024;
 static const int MAX_THREADS = 1024;
 static const size_t DYN_SMEM_BYTES = 256 * 1024;
 
+/*
+ * Warp collectives.  Lanes deposit a value together with the member mask they name; a group is released when every
+ * live lane of a mask has arrived naming that same mask, so disjoint sub-groups of a warp (k_lc.cu: four blocks of
+ * eight lanes) run their collectives independently of each other, as on the device.  On release every member gets a
+ * private copy of the group's values: a fast lane may deposit for its next collective before a slow one has read.
+ */
 struct Warp {
 	uint64_t val[32];
-	uint32_t alive, arrived, part, mask;
-	int phase, left;			/* phase 0: collecting deposits, 1: participants copy out */
+	uint32_t lmask[32];			/* the mask each arrived lane named */
+	uint32_t done[32];			/* members of the released collective this lane took part in, 0: not released */
+	uint64_t outv[32][32];
+	uint32_t alive, arrived;
 };
 struct Fiber {
 	void *sp;
@@ -96,15 +104,31 @@ void note_progress() { blk->ticks++; }
 
 static inline void yield() { emu_switch(&curf->sp, blk->sched_sp); }
 
-static void warp_try_release(Warp &w)
+static void warp_try_release(Warp &w, uint32_t mask)
 {
-	const uint32_t need = w.mask & w.alive;
-	if (w.phase == 0 && w.arrived != 0 && (w.arrived & need) == need) {
-		w.phase = 1;
-		w.part = w.arrived;
-		w.left = __builtin_popcount(w.arrived);
-		blk->ticks++;
+	const uint32_t need = mask & w.alive;
+	if (need == 0 || (w.arrived & need) != need)
+		return;
+	for (int l = 0; l < 32; l++)
+		if (((need >> l) & 1u) && w.lmask[l] != mask)
+			return;			/* that lane waits in another collective */
+	for (int p = 0; p < 32; p++) {
+		if (!((need >> p) & 1u))
+			continue;
+		for (int l = 0; l < 32; l++)	/* reading a lane that does not take part is undefined in CUDA: poison it */
+			w.outv[p][l] = ((need >> l) & 1u) ? w.val[l] : 0xDEADBEEFCAFEF00Dull;
+		w.done[p] = need;
 	}
+	w.arrived &= ~need;
+	blk->ticks++;
+}
+
+/* a lane left (exit): groups that only waited for it are complete now */
+static void warp_recheck(Warp &w)
+{
+	for (int l = 0; l < 32; l++)
+		if ((w.arrived >> l) & 1u)
+			warp_try_release(w, w.lmask[l]);
 }
 
 static void fiber_exit()
@@ -116,7 +140,7 @@ static void fiber_exit()
 	b->ticks++;
 	Warp &w = *f->ctx.warp;
 	w.alive &= ~(1u << f->ctx.lane);
-	warp_try_release(w);			/* the lanes still waiting no longer wait for this one */
+	warp_recheck(w);			/* the lanes still waiting no longer wait for this one */
 	if (b->bar_arrived > 0 && b->bar_arrived == b->alive) {	/* an exited thread counts as arrived */
 		b->bar_arrived = 0;
 		b->bar_gen++;
@@ -155,28 +179,21 @@ uint32_t warp_collect(uint32_t mask, uint64_t v, uint64_t out[32])
 	Fiber *f = curf;
 	Warp &w = *f->ctx.warp;
 	const int lane = f->ctx.lane;
-	while (w.phase == 1) {			/* the previous collective is still being read by its participants */
-		f->wait = WAIT_DRAIN;
-		yield();
-	}
 	w.val[lane] = v;
+	w.lmask[lane] = mask;
+	w.done[lane] = 0;
 	w.arrived |= 1u << lane;
-	w.mask = mask;
 	blk->ticks++;
-	warp_try_release(w);
-	while (!(w.phase == 1 && ((w.part >> lane) & 1u))) {
+	warp_try_release(w, mask);
+	while (w.done[lane] == 0) {
 		f->wait = WAIT_WARP;
 		yield();
 	}
 	f->wait = RUN;
-	const uint32_t part = w.part;
-	for (int l = 0; l < 32; l++)		/* reading a lane that does not take part is undefined in CUDA: poison it */
-		out[l] = ((part >> l) & 1u) ? w.val[l] : 0xDEADBEEFCAFEF00Dull;
-	if (--w.left == 0) {
-		w.phase = 0;
-		w.arrived = 0;
-		blk->ticks++;
-	}
+	const uint32_t part = w.done[lane];
+	w.done[lane] = 0;
+	for (int l = 0; l < 32; l++)
+		out[l] = w.outv[lane][l];
 	return part;
 }
 
@@ -187,8 +204,7 @@ static inline bool runnable(const Block *b, const Fiber *f)
 	const Warp &w = *f->ctx.warp;
 	switch (f->wait) {
 	case WAIT_BAR: return b->bar_gen != f->bar_seen;
-	case WAIT_WARP: return w.phase == 1 && ((w.part >> f->ctx.lane) & 1u);
-	case WAIT_DRAIN: return w.phase == 0;
+	case WAIT_WARP: return w.done[f->ctx.lane] != 0;
 	default: return true;
 	}
 }
@@ -208,8 +224,8 @@ static void run_block(Block *b, dim3 grid, dim3 block, uint3 bid, size_t smem)
 		Warp &W = b->warps[w];
 		const int lanes = n - 32 * w >= 32 ? 32 : n - 32 * w;
 		W.alive = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1u);
-		W.arrived = W.part = W.mask = 0;
-		W.phase = W.left = 0;
+		W.arrived = 0;
+		memset(W.done, 0, sizeof(W.done));
 	}
 	for (int t = 0; t < n; t++) {
 		Fiber &f = b->fib[t];
