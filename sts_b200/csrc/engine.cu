@@ -722,6 +722,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 			if (S.k_ev1[k]) cudaEventDestroy(S.k_ev1[k]);
 		}
 	}
+	cudaFree(ctx->d_lcg_pow32);
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
 	cudaFree(ctx->d_tally);
 	cudaFree(ctx->d_assess_stage);
@@ -1076,7 +1077,13 @@ extern "C" int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_
 	int rc = next_slot(ctx, nstreams, &S);
 	if (rc) return rc;
 	if (first_stream < 0) return STSGPU_E_INVAL;
-	cudaError_t e = launch_lcg(ctx->P, S->d_in, first_stream, nstreams, S->s_light);
+	if (ctx->d_lcg_pow32 == nullptr) {
+		uint32_t tab[256];
+		lcg_pow32_table(tab);
+		CK(cudaMalloc((void **) &ctx->d_lcg_pow32, sizeof(tab)));
+		CK(cudaMemcpy(ctx->d_lcg_pow32, tab, sizeof(tab), cudaMemcpyHostToDevice));
+	}
+	cudaError_t e = launch_lcg(ctx->P, S->d_in, first_stream, nstreams, ctx->d_lcg_pow32, S->s_light);
 	if (e != cudaSuccess) {
 		set_err(ctx, "lcg", e);
 		return STSGPU_E_CUDA;

@@ -78,6 +78,7 @@ struct stsgpu_ctx {
 	double2 *dft_tabs[12] = { nullptr };
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
+	uint32_t *d_lcg_pow32 = nullptr;	/* k_lcg.cu: a^(32 j) mod p, made on first use */
 
 	/* assessment tallies (stsgpu_assess_*): per column [sample, toolow, freq[bins]] */
 	bool assessing = false;
@@ -113,5 +114,7 @@ cudaError_t launch_assess_add(const DevParams &P, int pv_off, int pv_cnt, const 
 			      int64_t bins, double alpha, unsigned long long *d_tally, cudaStream_t stream);
 cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha, double level, double lgam, const unsigned long long *d_tally,
 				 stsgpu_metric *d_out, cudaStream_t stream);
-cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, cudaStream_t stream);
+cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, const uint32_t *d_pow32,
+		       cudaStream_t stream);
+void lcg_pow32_table(uint32_t tab[256]);
 cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits, uint32_t *d_out);

@@ -38,7 +38,7 @@ def to_bytes(r, k):
 
 agg = {}
 for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "")
+    name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
     a = agg.setdefault(name, dict(n=0, us=0.0, rd=0.0, wr=0.0, alu=0.0, fp64=0.0, lsu=0.0, issue=0.0, occ=0.0, regs=0))
     us = to_us(r, "gpu__time_duration.sum")
     a["n"] += 1
@@ -55,7 +55,7 @@ for r in rows[2:]:
 
 # launches of each kernel in ONE batch of B streams (the capture window may straddle two batches: every kernel is
 # scaled to its per-batch launch count, i.e. average launch x launches per batch)
-per_batch = {"dft_cols16": max(1, B // 128), "dft_rows16": max(1, B // 128)}
+per_batch = {"dft_cols16": max(1, B // 128), "dft_rows16": max(1, B // 128), "dft_rows16_tma": max(1, B // 128)}
 for name, a in agg.items():
     want = per_batch.get(name, 1)
     if a["n"] != want:
@@ -65,8 +65,9 @@ for name, a in agg.items():
         a["n"] = want
 stream_bytes = n // 8
 alg = {  # algorithmic bytes per stream of one launch of the kernel
-    "dft_cols16": stream_bytes + 16 * (n // 2), "dft_rows16": 16 * (n // 2),
+    "dft_cols16": stream_bytes + 16 * (n // 2), "dft_rows16": 16 * (n // 2), "dft_rows16_tma": 16 * (n // 2),
     "universal_kernel": 113120 if n == 1 << 20 else stream_bytes,
+    "universal_dist_kernel": 113120 if n == 1 << 20 else stream_bytes, "universal_sum_kernel": 0,
     "tails_slots_kernel": 0, "tails_cusum_kernel": 0, "tails_apen_kernel": 0, "cyclic_hist_kernel": 0,
 }
 print("| kernel | launches | total us | algorithmic GB/s | of %.0f GB/s HBM (measured) | DRAM traffic / algorithmic | "
@@ -83,10 +84,29 @@ for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
         name, a["n"], us, gbs, gbs / peak, traf, a["alu"] / us, a["fp64"] / us, a["lsu"] / us, a["issue"] / us,
         a["occ"] / us, a["regs"]))
 if len(sys.argv) > 4:
-    groups = {"dft": ["dft_cols16", "dft_rows16"]}
-    out = {"streams": B, "bits": n, "source": os.path.basename(raw), "dram_bytes_per_group": {}}
+    # the summary bench.py quotes (roofline.traffic, roofline_all[].frac of the integer / shared-memory pipes): keyed by
+    # bench.py's kernel group names and stamped with the hash of the CUDA sources the capture was taken on
+    sys.path.insert(0, ROOT)
+    import bench
+    groups = {"dft": ["dft_cols16", "dft_rows16", "dft_rows16_tma"], "linear_complexity": ["lc_kernel_win", "lc_kernel_reg", "lc_kernel_warp"],
+              "rank": ["rank_kernel"], "pattern(serial,apen)": ["cyclic_hist16_kernel", "cyclic_hist_kernel"],
+              "universal": ["universal_dist_kernel", "universal_sum_kernel", "universal_kernel"],
+              "scan(freq,cusum,runs,excursions)": ["scan_kernel"],
+              "blocks(blockfreq,longestrun,overlapping)": ["block_frequency_kernel", "longest_run_kernel", "overlapping_kernel"],
+              "nonoverlapping": ["nonoverlapping_kernel"],
+              "tails(p-values)": ["tails_slots_kernel", "tails_cusum_kernel", "tails_apen_kernel"]}
+    pipe_of = {"linear_complexity": "alu", "rank": "alu", "pattern(serial,apen)": "lsu", "nonoverlapping": "lsu"}
+    out = {"streams": B, "bits": n, "source": os.path.basename(raw), "source_sha256": bench.csrc_sha256(),
+           "dram_bytes_per_group": {}, "pipe_util_pct": {}, "kernel_us_per_group": {}}
     for g, ks in groups.items():
-        out["dram_bytes_per_group"][g] = sum(agg[k]["rd"] + agg[k]["wr"] for k in ks if k in agg)
+        have = [k for k in ks if k in agg]
+        if not have:
+            continue
+        us = sum(agg[k]["us"] for k in have)
+        out["dram_bytes_per_group"][g] = sum(agg[k]["rd"] + agg[k]["wr"] for k in have)
+        out["kernel_us_per_group"][g] = round(us, 1)
+        if g in pipe_of and us > 0:
+            out["pipe_util_pct"][g] = round(sum(agg[k][pipe_of[g]] for k in have) / us, 1)
     json.dump(out, open(sys.argv[4], "w"), indent=1)
 print("\nsum of kernel durations: %.1f us for %d streams of %d bits -> %.1f Gbit/s if run back to back" % (
     tot, B, n, B * n / (tot * 1e-6) / 1e9))
