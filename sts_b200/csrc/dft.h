@@ -11,7 +11,7 @@ struct DftPlan {
 	int rad1[DFT_MAX_PASSES], rad2[DFT_MAX_PASSES];
 	int cw;			/* columns per CTA in the column pass */
 	int threads;		/* CTA size of the generic kernels (256 or 512) */
-	int fast;		/* 1: n = 2^20, the kernels of k_dft_fast.cu; 2: n = 10^6, k_dft_1e6.cu; 3: any n, k_dft_any.cu; 0: generic */
+	int fast;		/* 1: n = 2^20, the kernels of k_dft_fast.cu; 2: n = 10^6, k_dft_1e6.cu; 3: any n, k_dft_any.cu; 4: n = 10^7, k_dft_1e7.cu; 0: generic */
 	/* per-pass twiddles, pass p at offset off[p]: entry (r - 1) Ns + k = exp(-2 pi i k r / (Ns R)), so that
 	 * consecutive butterflies (consecutive k) read consecutive table entries */
 	const double2 *w1;
@@ -37,6 +37,16 @@ struct DftPlan {
 	const double2 *m_e2;	/* [1000]: exp(-2 pi i 50 j2 / N) */
 	const double2 *m_p1;	/* [500]:  exp(-2 pi i k1 / n) */
 	const double2 *m_p2;	/* [1000]: exp(-2 pi i 500 k2 / n) */
+	/* tables of the n = 10^7 kernels (k_dft_1e7.cu, N = 2000 x 2500, fast == 4), NULL otherwise */
+	const double2 *v_twA;	/* [9][10]:   exp(-2 pi i k r / 100),  r = 1..9, k < 10   (Ns = 10, columns and rows) */
+	const double2 *v_twB;	/* [9][100]:  exp(-2 pi i k r / 1000), k < 100            (column pass, Ns = 100) */
+	const double2 *v_twC;	/* [1000]:    exp(-2 pi i k / 2000)                       (column pass, radix 2, Ns = 1000) */
+	const double2 *v_rtwB;	/* [4][100]:  exp(-2 pi i k r / 500),  r = 1..4, k < 100  (row pass, radix 5, Ns = 100) */
+	const double2 *v_rtwC;	/* [4][500]:  exp(-2 pi i k r / 2500), k < 500            (row pass, radix 5, Ns = 500) */
+	const double2 *v_e1;	/* [200][2500]: exp(-2 pi i j2 t / N) */
+	const double2 *v_e2;	/* [2500]: exp(-2 pi i 200 j2 / N) */
+	const double2 *v_p1;	/* [2000]: exp(-2 pi i k1 / n) */
+	const double2 *v_p2;	/* [500]:  exp(-2 pi i 2000 j / n) */
 	/* Bluestein path for n/2 that is not 5-smooth (k_dft_any.cu, fast == 3), NULL / 0 otherwise */
 	long long bs_M;		/* convolution length, the power of two >= 2 N - 1 */
 	int bs_logM;

@@ -580,10 +580,17 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	if (en & (1u << STSGPU_TEST_DFT)) {
 		DftPlan &D = ctx->dft;				/* N1, N2, radix lists: dft_make_plan above */
 		const bool any = D.fast == 3;			/* Bluestein (k_dft_any.cu): n/2 is not 5-smooth */
+		const bool ten_million = !any && n == 10000000 && !(getenv("STSGPU_DFT_GENERIC") && atoi(getenv("STSGPU_DFT_GENERIC")) > 0);
+		if (ten_million) {			/* BASELINE config 4: the split k_dft_1e7.cu is written for */
+			D.N1 = 2000;
+			D.N2 = 2500;
+		}
 		const int N1 = any ? 1 : D.N1, N2 = any ? 1 : D.N2;
 		const int64_t N = any ? D.bs_M : (int64_t) N1 * N2;	/* elements of one stream in a work buffer */
 		if (!any)
 			D.fast = (n == (1LL << 20)) ? 1 : (n == 1000000 ? 2 : 0);
+		if (ten_million)
+			D.fast = 4;
 		D.T = sqrt(log(20.0) * (double) n);				/* discreteFourierTransform.c:142 */
 		D.w1 = D.w2 = D.tl = D.th = D.p1 = D.p2 = nullptr;
 		D.bs_chirp = D.bs_bhat = D.bs_tw = D.bs_wq = nullptr;
@@ -669,6 +676,32 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 			CKC(upload(&d, m.data(), m.size()), "upload(fft 1e6 tables)"); ctx->dft_tabs[5] = d;
 			D.m_twA = d + o[0]; D.m_twB = d + o[1]; D.m_twC = d + o[2]; D.m_twD = d + o[3];
 			D.m_e1 = d + o[4]; D.m_e2 = d + o[5]; D.m_p1 = d + o[6]; D.m_p2 = d + o[7];
+		}
+		D.v_twA = D.v_twB = D.v_twC = D.v_rtwB = D.v_rtwC = D.v_e1 = D.v_e2 = D.v_p1 = D.v_p2 = nullptr;
+		if (D.fast == 4) {						/* n = 10^7: k_dft_1e7.cu (2000 x 2500), one allocation */
+			std::vector<double2> m;
+			size_t o[9];
+			o[0] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 10; k++) m.push_back(unit_root(k * r, 100));
+			o[1] = m.size();
+			for (int r = 1; r < 10; r++) for (int k = 0; k < 100; k++) m.push_back(unit_root(k * r, 1000));
+			o[2] = m.size();
+			for (int k = 0; k < 1000; k++) m.push_back(unit_root(k, 2000));
+			o[3] = m.size();
+			for (int r = 1; r < 5; r++) for (int k = 0; k < 100; k++) m.push_back(unit_root(k * r, 500));
+			o[4] = m.size();
+			for (int r = 1; r < 5; r++) for (int k = 0; k < 500; k++) m.push_back(unit_root(k * r, 2500));
+			o[5] = m.size();
+			for (int t = 0; t < 200; t++) for (int j2 = 0; j2 < 2500; j2++) m.push_back(unit_root((long double) j2 * t, (long double) N));
+			o[6] = m.size();
+			for (int j2 = 0; j2 < 2500; j2++) m.push_back(unit_root((long double) 200 * j2, (long double) N));
+			o[7] = m.size();
+			for (int k = 0; k < 2000; k++) m.push_back(unit_root(k, (long double) n));
+			o[8] = m.size();
+			for (int k = 0; k < 500; k++) m.push_back(unit_root((long double) 2000 * k, (long double) n));
+			CKC(upload(&d, m.data(), m.size()), "upload(fft 1e7 tables)"); ctx->dft_tabs[5] = d;
+			D.v_twA = d + o[0]; D.v_twB = d + o[1]; D.v_twC = d + o[2]; D.v_rtwB = d + o[3]; D.v_rtwC = d + o[4];
+			D.v_e1 = d + o[5]; D.v_e2 = d + o[6]; D.v_p1 = d + o[7]; D.v_p2 = d + o[8];
 		}
 		}	/* !any */
 		int64_t chunk = 128;

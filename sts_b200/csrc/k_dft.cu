@@ -32,6 +32,7 @@
 cudaError_t launch_dft_fast(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 cudaError_t launch_dft_1e6(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 cudaError_t launch_dft_any(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
+cudaError_t launch_dft_1e7(const DevParams &P, const LaunchCtx &L, const DftPlan &D, double2 *d_work, int64_t work_streams);
 
 
 /*
@@ -346,6 +347,8 @@ cudaError_t launch_dft(const DevParams &P, const LaunchCtx &L, const DftPlan &D,
 		return launch_dft_1e6(P, L, D, d_work, work_streams);
 	if (D.fast == 3)
 		return launch_dft_any(P, L, D, d_work, work_streams);
+	if (D.fast == 4)
+		return launch_dft_1e7(P, L, D, d_work, work_streams);
 	const size_t smem1 = (size_t) D.N1 * D.cw * sizeof(double2);
 	const size_t smem2 = (size_t) 2 * D.N2 * sizeof(double2);
 	cudaError_t e;
