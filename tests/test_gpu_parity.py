@@ -333,7 +333,10 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     (11, dict(n=1 << 20, apen_m=14)),                    # ApEn: H = 15
     (14, dict(n=1 << 21, serial_m=18)),                  # Serial: sliced 32-bit histogram, 8 slices
     (8, dict(n=1 << 18, non_overlapping_m=8)),
-    (8, dict(n=1 << 18, non_overlapping_m=12)),
+    (8, dict(n=1 << 18, non_overlapping_m=12)),              # wide-window stride 2
+    (8, dict(n=(1 << 18) + 8 * 13, non_overlapping_m=10)),   # stride 4 with a partial last group of window starts
+    (8, dict(n=1 << 18, non_overlapping_m=13)),              # stride 1 (2^13 bins already)
+    (8, dict(n=(1 << 19) - 8 * 5, non_overlapping_m=15)),    # largest m
     (2, dict(n=1 << 20, block_frequency_M=11000)),       # blocks that are not word aligned
     (7, dict(n=1 << 14)),                                # DFT: generic path, small power of two
     (7, dict(n=5 * (1 << 16))),                          # DFT: one radix-5 pass
