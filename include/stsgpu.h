@@ -268,6 +268,16 @@ int stsgpu_results_stats(stsgpu_ctx *ctx, const double **fstats);
  */
 int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_t nstreams);
 
+/*
+ * The same for any generator of tools/generators.c that can jump ahead - 1 (LCG, as above), 2 (quadratic
+ * congruential I, generators.c:915-975), 4 (cubic congruential, :1049-1108) and 5 (XOR, :1111-1186) - with every
+ * behaviour of the tool that shapes its output (csrc/k_gen.cu lists them): byte-identical to `generators <g> <count>`
+ * for n = 2^20.  n must be at least 1024.  Generators 3, 6, 7, 8 and 9 feed their whole state through a non-linear
+ * map once per block - one chain for the whole run, which no number of threads can shorten - and are made on a host
+ * core in front of stsgpu_submit (host/sts_generators.h); for them this call returns STSGPU_E_UNSUPPORTED.
+ */
+int stsgpu_generate(stsgpu_ctx *ctx, int generator, int64_t first_stream, int64_t nstreams);
+
 /* copy the device input buffer back (tests / fixtures) */
 int stsgpu_download_input(stsgpu_ctx *ctx, uint8_t *raw, int64_t nstreams);
 

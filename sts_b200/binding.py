@@ -20,7 +20,7 @@ TEST_NAMES = [None, "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "Lo
 
 # every symbol include/stsgpu.h declares (checked by tests/test_abi.py)
 EXPORTS = ["stsgpu_default_params", "stsgpu_create", "stsgpu_destroy", "stsgpu_get_layout", "stsgpu_query_layout", "stsgpu_dft_supported", "stsgpu_submit",
-           "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_results_stats", "stsgpu_generate_lcg",
+           "stsgpu_submit_resident", "stsgpu_submit_ascii", "stsgpu_ascii_status", "stsgpu_upload", "stsgpu_wait", "stsgpu_pending", "stsgpu_results", "stsgpu_results_stats", "stsgpu_generate_lcg", "stsgpu_generate",
            "stsgpu_download_input", "stsgpu_host_alloc", "stsgpu_host_free", "stsgpu_comm_unique_id",
            "stsgpu_comm_init", "stsgpu_gather_begin", "stsgpu_gather_pvals", "stsgpu_comm_barrier", "stsgpu_assess_begin",
            "stsgpu_assess_add", "stsgpu_assess_reduce", "stsgpu_assess_finish", "stsgpu_set_profiling",
@@ -99,6 +99,7 @@ def load_library():
     lib.stsgpu_results.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.stsgpu_results_stats.argtypes = [vp, C.POINTER(vp)]
     lib.stsgpu_generate_lcg.argtypes = [vp, i64, i64]
+    lib.stsgpu_generate.argtypes = [vp, C.c_int, i64, i64]
     lib.stsgpu_download_input.argtypes = [vp, vp, i64]
     lib.stsgpu_host_alloc.argtypes = [C.c_size_t]
     lib.stsgpu_host_alloc.restype = vp
@@ -277,6 +278,10 @@ class Engine:
     # ---- synthetic input ----
     def generate_lcg(self, first_stream, nstreams):
         self._ck(self.lib.stsgpu_generate_lcg(self.h, first_stream, nstreams), "generate_lcg")
+
+    def generate(self, generator, first_stream, nstreams):
+        """generators 1, 2, 4, 5 of tools/generators.c into the device input buffer (stsgpu_generate)"""
+        self._ck(self.lib.stsgpu_generate(self.h, generator, first_stream, nstreams), "generate")
 
     def download_input(self, nstreams):
         out = np.zeros(nstreams * self.params.n // 8, dtype=np.uint8)

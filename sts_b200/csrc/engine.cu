@@ -756,6 +756,7 @@ extern "C" void stsgpu_destroy(stsgpu_ctx *ctx)
 		}
 	}
 	cudaFree(ctx->d_lcg_pow32);
+	cudaFree(ctx->d_gen_consts);
 	cudaFree(ctx->d_templates); cudaFree(ctx->d_class_lut); cudaFree(ctx->d_log2tab); cudaFree(ctx->d_debug);
 	cudaFree(ctx->d_tally);
 	cudaFree(ctx->d_assess_stage);
@@ -1119,6 +1120,51 @@ extern "C" int stsgpu_generate_lcg(stsgpu_ctx *ctx, int64_t first_stream, int64_
 	cudaError_t e = launch_lcg(ctx->P, S->d_in, first_stream, nstreams, ctx->d_lcg_pow32, S->s_light);
 	if (e != cudaSuccess) {
 		set_err(ctx, "lcg", e);
+		return STSGPU_E_CUDA;
+	}
+	ctx->launches += 1;
+	return STSGPU_OK;
+}
+
+extern "C" int stsgpu_generate(stsgpu_ctx *ctx, int generator, int64_t first_stream, int64_t nstreams)
+{
+	if (ctx == NULL)
+		return STSGPU_E_INVAL;
+	if (generator == 1)
+		return stsgpu_generate_lcg(ctx, first_stream, nstreams);
+	if (generator == 3 || (generator >= 6 && generator <= 9)) {
+		snprintf(ctx->err, sizeof(ctx->err), "generator %d is one chain for the whole run: made on the host (host/sts_generators.h)",
+			 generator);
+		return STSGPU_E_UNSUPPORTED;
+	}
+	if (generator != 2 && generator != 4 && generator != 5)
+		return STSGPU_E_INVAL;
+	if (ctx->P.n < 1024) {
+		snprintf(ctx->err, sizeof(ctx->err), "generator %d needs n >= 1024", generator);
+		return STSGPU_E_UNSUPPORTED;
+	}
+	Slot *S;
+	int rc = next_slot(ctx, nstreams, &S);
+	if (rc) return rc;
+	if (first_stream < 0) return STSGPU_E_INVAL;
+	if (ctx->d_gen_consts == nullptr) {
+		void *h = malloc(gen_consts_bytes());
+		if (h == NULL) return STSGPU_E_NOMEM;
+		gen_consts_host(h);
+		cudaError_t e = cudaMalloc(&ctx->d_gen_consts, gen_consts_bytes());
+		if (e == cudaSuccess)
+			e = cudaMemcpy(ctx->d_gen_consts, h, gen_consts_bytes(), cudaMemcpyHostToDevice);
+		free(h);
+		if (e != cudaSuccess) {
+			cudaFree(ctx->d_gen_consts);
+			ctx->d_gen_consts = nullptr;
+			set_err(ctx, "generator tables", e);
+			return STSGPU_E_CUDA;
+		}
+	}
+	cudaError_t e = launch_generator(generator, ctx->P, S->d_in, first_stream, nstreams, ctx->d_gen_consts, S->s_light);
+	if (e != cudaSuccess) {
+		set_err(ctx, "generator", e);
 		return STSGPU_E_CUDA;
 	}
 	ctx->launches += 1;

@@ -79,6 +79,7 @@ struct stsgpu_ctx {
 	int64_t dft_chunk = 0;
 	uint32_t *d_debug = nullptr;
 	uint32_t *d_lcg_pow32 = nullptr;	/* k_lcg.cu: a^(32 j) mod p, made on first use */
+	void *d_gen_consts = nullptr;		/* k_gen.cu: moduli, seeds and tables of generators 2, 4 and 5, made on first use */
 
 	/* assessment tallies (stsgpu_assess_*): per column [sample, toolow, freq[bins]] */
 	bool assessing = false;
@@ -117,4 +118,9 @@ cudaError_t launch_assess_finish(const DevParams &P, int64_t bins, double alpha,
 cudaError_t launch_lcg(const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams, const uint32_t *d_pow32,
 		       cudaStream_t stream);
 void lcg_pow32_table(uint32_t tab[256]);
+/* k_gen.cu: generators 2, 4, 5 */
+size_t gen_consts_bytes(void);
+void gen_consts_host(void *dst);
+cudaError_t launch_generator(int generator, const DevParams &P, uint32_t *d_in, int64_t first_stream, int64_t nstreams,
+			     const void *d_consts, cudaStream_t stream);
 cudaError_t launch_debug_histogram(const DevParams &P, const LaunchCtx &L, int64_t stream_index, int bits, uint32_t *d_out);

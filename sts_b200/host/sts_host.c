@@ -16,6 +16,7 @@
 #include <time.h>
 #include <unistd.h>
 #include "sts_host.h"
+#include "sts_generators.h"
 
 const char *const sts_testNames[STS_NUMOFTESTS + 1] = {	/* parse_args.c:170-187 */
 	"((all_tests))", "Frequency", "BlockFrequency", "CumulativeSums", "Runs", "LongestRun", "Rank", "DFT",
@@ -457,14 +458,16 @@ sts_invokeTestSuite(struct sts_state *s)
 	const long n = s->tp.n;
 	const long nb = n / 8;
 	const long B = s->batchStreams < s->tp.numOfBitStreams ? s->batchStreams : s->tp.numOfBitStreams;
-	const bool generated = (s->generator == 1);
-	const bool from_stdin = !generated && (strcmp(s->randomDataPath, "-") == 0);
-	const bool gpu_ascii = !generated && (s->dataFormat == STS_FORMAT_ASCII_01) && !from_stdin;
-	s->streamFile = generated ? NULL : (from_stdin ? stdin : fopen(s->randomDataPath, "rb"));
-	if (s->streamFile == NULL && !generated)
+	const bool chained = sts_gen_is_chained((int) s->generator);	/* 3, 6, 7, 8, 9: one host thread, sts_generators.c */
+	const bool generated = (s->generator != 0) && !chained;		/* 1, 2, 4, 5: made on the GPU */
+	const bool no_file = generated || chained;
+	const bool from_stdin = !no_file && (strcmp(s->randomDataPath, "-") == 0);
+	const bool gpu_ascii = !no_file && (s->dataFormat == STS_FORMAT_ASCII_01) && !from_stdin;
+	s->streamFile = no_file ? NULL : (from_stdin ? stdin : fopen(s->randomDataPath, "rb"));
+	if (s->streamFile == NULL && !no_file)
 		sts_err(210, __func__, "cannot open data file %s: %s", s->randomDataPath, strerror(errno));
 	long base_seek = 0, file_size = 0;
-	if (!from_stdin && !generated) {
+	if (!from_stdin && !no_file) {
 		const long per_stream = (s->dataFormat == STS_FORMAT_RAW_BINARY) ? nb : n;
 		base_seek = s->jobnum * per_stream * s->tp.numOfBitStreams;
 		if (fseek(s->streamFile, 0, SEEK_END) != 0 || (file_size = ftell(s->streamFile)) < 0 ||
@@ -482,6 +485,18 @@ sts_invokeTestSuite(struct sts_state *s)
 	}
 	struct sts_thread_state ts = { 0, s, 0, NULL };
 	const long total = s->tp.numOfBitStreams;
+	struct sts_gen *chain = NULL;
+	if (chained) {
+		chain = sts_gen_open((int) s->generator, n);
+		if (chain == NULL)
+			sts_err(218, __func__, "cannot start generator %ld for streams of %ld bits", s->generator, n);
+		/* job `jobnum` tests streams [jobnum * iterations, ...) of the tool's output: a chain has to be run up to there */
+		for (long skip = s->jobnum * total; skip > 0;) {
+			const long k = skip < B ? skip : B;
+			sts_gen_next(chain, buf[0], k);
+			skip -= k;
+		}
+	}
 	double t_read = 0.0, t_wait = 0.0, t_keep = 0.0;
 	const double t_begin = now_s();
 	long submitted = 0, done = 0;
@@ -500,9 +515,12 @@ sts_invokeTestSuite(struct sts_state *s)
 			if (generated) {
 				/* job `jobnum` of the reference's distributed mode would read streams [jobnum * iterations, ...) of
 				 * the generator's file: skip ahead to the same place */
-				rc = stsgpu_generate_lcg(s->engine, s->jobnum * total + submitted, want);
+				rc = stsgpu_generate(s->engine, (int) s->generator, s->jobnum * total + submitted, want);
 				if (rc == STSGPU_OK)
 					rc = stsgpu_submit_resident(s->engine, want, submitted);
+			} else if (chained) {
+				rc = sts_gen_next(chain, buf[w % depth], want) == 0 ? stsgpu_submit(s->engine, buf[w % depth], want, submitted)
+										     : STSGPU_E_INVAL;
 			} else if (gpu_ascii) {
 				const long off = base_seek + submitted * n;
 				long len = (want + 1) * n;
@@ -586,8 +604,9 @@ sts_invokeTestSuite(struct sts_state *s)
 	s->tp.numOfBitStreams = done;		/* ASCII input may end early (utilities.c:1693-1700) */
 	for (int i = 0; i < depth; i++)
 		stsgpu_host_free(buf[i]);
-	if (!from_stdin && !generated)
+	if (!from_stdin && !no_file)
 		fclose(s->streamFile);
+	sts_gen_close(chain);
 	s->streamFile = NULL;
 }
 

@@ -16,11 +16,12 @@
 static const char *usage =
 	"usage: stsb200 [-v level] [-t test1[,test2]..] [-P num=value[,num=value]..] [-S bitcount] [-i iterations]\n"
 	"               [-I reportCycle] [-O] [-s] [-w workDir] [-F r|a] [-j jobnum] [-m b|i|a] [-d pvaluesdir] [-T threads]\n"
-	"               [-B batch] [-D device] [-g 0|1] [datafile | -]\n"
+	"               [-B batch] [-D device] [-g 0..9] [datafile | -]\n"
 	"  same meanings as sts (arcetri/sts 3.2.7); -B (streams per GPU batch) and -D (CUDA device) are new.\n"
 	"  -m i iterates on the GPU and writes workDir/sts.JJJJ.<iterations>.<n>.pvalues; -m b iterates and writes the\n"
 	"  reference's result.txt (with -O the table of its legacy finalAnalysisReport.txt) from tallies kept on the GPU,\n"
-	"  without keeping the p-values; -g 1 tests the linear congruential generator of tools/generators, made on the GPU;\n"
+	"  without keeping the p-values; -g 1..9 tests the output of generator g of tools/generators instead of a file:\n"
+	"  1, 2, 4, 5 are made on the GPU (any job jumps to its streams), 3, 6, 7, 8, 9 are one chain and run on a host core;\n"
 	"  -m a -d dir assesses the .pvalues files of earlier -m i runs, streamed through the GPU tallies in bounded memory.\n";
 
 int
@@ -79,10 +80,10 @@ main(int argc, char **argv)
 			else sts_err(1, __func__, "-m mode: %s must be b, i or a", optarg);
 			break;
 		case 'd': free(st.pvalues_dir); st.pvalues_dir = strdup(optarg); break;
-		case 'g':	/* sts 3 only accepts -g 0 (parse_args.c:480-483); generator 1 of tools/generators.c runs on the GPU here */
+		case 'g':	/* sts 3 only accepts -g 0 (parse_args.c:480-483); here 1..9 are the generators of tools/generators.c */
 			st.generator = atol(optarg);
-			if (st.generator != 0 && st.generator != 1)
-				sts_err(1, __func__, "-g generator: %ld must be 0 (data file) or 1 (linear congruential, made on the GPU)", st.generator);
+			if (st.generator < 0 || st.generator > 9)
+				sts_err(1, __func__, "-g generator: %ld must be 0 (data file) or 1..9 (tools/generators)", st.generator);
 			break;
 		case 'T': st.numberOfThreads = atol(optarg); break;
 		case 'B': st.batchStreams = atol(optarg); break;
@@ -99,6 +100,14 @@ main(int argc, char **argv)
 		st.randomDataPath = strdup(argv[optind]);
 	else if (optind == argc && st.generator == 1)
 		st.randomDataPath = strdup("((tools/generators 1, linear congruential, generated on the GPU))");
+	else if (optind == argc && st.generator >= 2) {
+		static const char *names[10] = { "", "", "quadratic congruential I", "quadratic congruential II", "cubic congruential", "XOR",
+			"modular exponentiation", "Blum-Blum-Shub", "Micali-Schnorr", "SHA-1 based" };
+		char label[128];
+		snprintf(label, sizeof(label), "((tools/generators %ld, %s, generated on the %s))", st.generator, names[st.generator],
+			 (st.generator == 2 || st.generator == 4 || st.generator == 5) ? "GPU" : "host");
+		st.randomDataPath = strdup(label);
+	}
 	else if (optind != argc || st.runMode != STS_MODE_ASSESS_ONLY) {	/* parse_args.c:706-732: -m a needs no data file */
 		fputs(usage, stderr);
 		return 1;

@@ -50,7 +50,7 @@ def emu_host_driver():
     build = os.path.dirname(lib)
     exe = os.path.join(build, "stsb200_emu")
     host = os.path.join(ROOT, "sts_b200", "host")
-    srcs = [os.path.join(host, "stsb200.c"), os.path.join(host, "sts_host.c")]
+    srcs = [os.path.join(host, "stsb200.c"), os.path.join(host, "sts_host.c"), os.path.join(host, "sts_generators.c")]
     deps = srcs + [os.path.join(host, "sts_host.h"), lib]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         asan = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("STS_EMU_ASAN", "") not in ("", "0") else []

@@ -42,3 +42,4 @@ test_dash_s_results_and_data_files_identical_to_reference = _again(H.test_dash_s
 test_generator_1_on_the_device = _again(H.test_generator_1_on_the_device)
 test_ascii_file_against_committed_reference_reading = _again(H.test_ascii_file_against_committed_reference_reading)
 test_reports_against_committed_reference_bodies = _again(H.test_reports_against_committed_reference_bodies)
+test_generators_2_to_9_are_the_files_the_tool_writes = _again(H.test_generators_2_to_9_are_the_files_the_tool_writes)

@@ -57,6 +57,9 @@ def test_full_batch_properties_and_sampled_parity(sts, oracle, monkeypatch):    
     G.test_full_batch_properties_and_sampled_parity(sts, oracle)
 test_stats_flag_last_cycle_counters_and_fstats = _pick(G.test_stats_flag_last_cycle_counters_and_fstats, lambda n: True)
 test_device_lcg_is_the_reference_generator = _rebind(G.test_device_lcg_is_the_reference_generator, "")
+test_device_generators_match_the_reference_tool_and_jump_ahead = _pick(
+    G.test_device_generators_match_the_reference_tool_and_jump_ahead, lambda gen: True)
+test_chained_generators_are_refused_by_the_device = _rebind(G.test_chained_generators_are_refused_by_the_device, "")
 test_cyclic_pattern_histogram = _pick(G.test_cyclic_pattern_histogram, lambda bits: bits in (3, 16, 18))
 test_pipelined_batches_complete_in_order = _rebind(G.test_pipelined_batches_complete_in_order, "")
 test_assessment_tallies_match_reference_report = _rebind(G.test_assessment_tallies_match_reference_report, "")

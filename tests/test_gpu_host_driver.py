@@ -251,6 +251,31 @@ def test_generator_1_on_the_device(tmp_path, oracle):
     assert not [f for f in os.listdir(str(tmp_path / "made")) if f.endswith(".pvalues")]     # sts.c:358: only -m i writes them
 
 
+@pytest.mark.parametrize("gen", [2, 3, 4, 5, 6, 7, 8, 9])
+def test_generators_2_to_9_are_the_files_the_tool_writes(tmp_path, gen):
+    """-g 2..9: testing a generator equals testing the file tools/generators writes for it (restated by the oracle, which
+    is pinned to the tool's output): 2, 4, 5 made on the GPU, 3, 6, 7, 8, 9 chained on a host core; job 1 of two starts
+    at its own streams either way.  Generator 8 is the tool's with its uninitialised accumulator defined as zero."""
+    from oracle import generators as OG
+    n, its = (1 << 20, 4) if gen not in (6, 7) else (1 << 14, 4)        # 6 and 7 take seconds per megabit stream
+    tests = "1,2,3,4" if n == 1 << 20 else "1,3,4"
+    p = str(tmp_path / "gen.bin")
+    open(p, "wb").write(b"".join(OG.generate(gen, n, its)))
+    size = ["-S", str(n)]
+    run([STSB200, "-m", "i", "-i", str(its), "-t", tests, "-F", "r", "-w", str(tmp_path / "file")] + size + [p])
+    run([STSB200, "-g", str(gen), "-m", "i", "-i", str(its), "-B", "3", "-t", tests, "-w", str(tmp_path / "made")] + size)
+    name = "sts.0000.%d.%d.pvalues" % (its, n)
+    a, b = read_pvalues(str(tmp_path / "file" / name)), read_pvalues(str(tmp_path / "made" / name))
+    assert sorted(a) == sorted(b)
+    for t in a:
+        assert (a[t] == b[t]).all(), "test %d" % t
+    run([STSB200, "-g", str(gen), "-m", "i", "-j", "1", "-i", str(its // 2), "-t", tests, "-w", str(tmp_path / "job1")] + size)
+    c = read_pvalues(str(tmp_path / "job1" / ("sts.0001.%d.%d.pvalues" % (its // 2, n))))
+    for t in a:
+        per = len(a[t]) // its
+        assert (c[t] == a[t][per * (its // 2):]).all(), "test %d" % t
+
+
 def test_ascii_file_against_committed_reference_reading(tmp_path, oracle):
     """the same as test_ascii_file_with_line_breaks_matches_reference, but against the committed fixture
     (tests/golden/ascii_lines80_3.npz, made by the reference binary) so that it also runs where oracle/_ref is absent"""

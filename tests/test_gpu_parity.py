@@ -171,6 +171,39 @@ def test_device_lcg_is_the_reference_generator(sts, oracle):
         assert (eng.download_input(2) == oracle.lcg_bytes(1, 2, 1000008)).all()
 
 
+@pytest.mark.parametrize("gen", [2, 4, 5])
+def test_device_generators_match_the_reference_tool_and_jump_ahead(sts, gen):
+    """generators 2, 4, 5 of tools/generators.c made on the device (csrc/k_gen.cu): the first streams against the
+    vectors of the unmodified tool, then streams far into the tool's output and ragged lengths against the oracle
+    (oracle/generators.py, itself pinned to the same vectors) - every stream and every segment of a stream starts
+    from its own jump, so a stream made alone equals the same stream made as part of a longer run"""
+    import hashlib
+    import json
+    from oracle import generators as OG
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generators.json")))[str(gen)]
+    k = len(gold["sha256"])
+    with sts.Engine(max_streams=4) as eng:
+        eng.generate(gen, 0, k)
+        got = eng.download_input(k).reshape(k, -1)
+        assert [hashlib.sha256(got[i].tobytes()).hexdigest() for i in range(k)] == gold["sha256"]
+        eng.generate(gen, k - 1, 1)                  # the last of them again, from its own jump
+        assert hashlib.sha256(eng.download_input(1).tobytes()).hexdigest() == gold["sha256"][k - 1]
+    for n, first, cnt in ((1024 * 40, 37, 3), (1000 * 8, 1, 2), (512 * 3 + 8, 5, 4), (4096 + 24, 0, 3)):
+        want = OG.generate(gen, n, first + cnt)[first:]
+        with sts.Engine(max_streams=4, n=n, test_mask=1 << 1) as eng:
+            eng.generate(gen, first, cnt)
+            got = eng.download_input(cnt).reshape(cnt, -1)
+        assert [got[i].tobytes() for i in range(cnt)] == want, (gen, n, first)
+
+
+def test_chained_generators_are_refused_by_the_device(sts):
+    with sts.Engine(max_streams=1) as eng:
+        for gen in (3, 6, 7, 8, 9):
+            with pytest.raises(sts.EngineError, match="host"):
+                eng.generate(gen, 0, 1)
+        eng.generate(1, 0, 1)                        # generator 1 is the LCG call
+
+
 @pytest.mark.parametrize("bits", [3, 9, 11, 16, 18])
 def test_cyclic_pattern_histogram(sts, oracle, bits):
     raw = oracle.lcg_bytes(3, 1)
