@@ -21,8 +21,9 @@
  * block and drops the unused end of its last one (copyBitsToEpsilon :704-760); generator 5 has no blocks.
  *
  * Work split: one thread per SEGMENT of a stream (GEN_SEGS per stream for 2 and 4, 1024 words for 5), each with its own
- * jump.  A jump costs about as much as 500 blocks of generator 2, so more segments mean more parallel threads and
- * more total work; four keep a batch of 1024 streams around the cost of the tests' fastest kernels.
+ * jump.  A jump costs as much as about 550 blocks of generator 2 (140 of generator 4), so more segments mean more
+ * threads and more total work; the device is otherwise idle while a batch is made, so the split is chosen for time:
+ * measured per 1024 streams of 2^20 bits with 4 segments 6.3 ms (2) and 3.5 ms (4), generator 5 0.29 ms, the LCG 1.4 ms.
  */
 #include <string.h>
 #include "common.cuh"
@@ -30,7 +31,7 @@
 
 #define GL 16				/* 32-bit limbs of a 512-bit number, least significant first */
 #define GEN_THREADS 32
-#define GEN_SEGS 4
+#define GEN_SEGS 16
 #define XOR_SEG_WORDS 1024
 
 struct GenConsts {
