@@ -28,7 +28,7 @@ def run(args, **kw):
     (["-P", "12=3", "f"], "-P num=value"),
     (["-i", "0", "f"], "-i iterations"),
     (["-m", "a"], "-m a requires -d"),
-    (["-g", "2"], "-g generator"),
+    (["-g", "10"], "-g generator"),
     (["-S", "992", "f"], "bitcount(n): 992 must >= 1000"),                 # parse_args.c:945-947
     (["-S", "1001", "f"], "bitcount(n): 1001 must be a multiple of 8"),    # parse_args.c:939-944
     (["-P", "9=104", "f"], "bitcount(n): 104 must >= 1000"),
