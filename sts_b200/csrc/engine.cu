@@ -480,6 +480,7 @@ extern "C" int stsgpu_create(const stsgpu_params *p, stsgpu_ctx **out)
 	} while (0)
 	ctx->nslots = p->pipeline_depth > 1 ? p->pipeline_depth : 1;
 	ctx->overlap_batches = !(getenv("STSGPU_SERIALIZE_BATCHES") && atoi(getenv("STSGPU_SERIALIZE_BATCHES")) > 0);
+	ctx->compute_inflight = getenv("STSGPU_COMPUTE_INFLIGHT") ? atoi(getenv("STSGPU_COMPUTE_INFLIGHT")) : 2;
 	if (ctx->nslots > STS_MAX_SLOTS) ctx->nslots = STS_MAX_SLOTS;
 	int prio_lo = 0, prio_hi = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);		/* lo = least urgent, hi = most urgent */
@@ -798,6 +799,12 @@ static int run_tests(stsgpu_ctx *ctx, Slot &S, int64_t nstreams, int64_t first_i
 	 */
 	if (ctx->nslots > 1 && ctx->submit_seq > 0 && !ctx->overlap_batches) {
 		Slot &prev = ctx->slots[(ctx->submit_seq - 1) % ctx->nslots];
+		CK(cudaStreamWaitEvent(sl, prev.ev_kdone, 0));
+	} else if (ctx->compute_inflight > 0 && ctx->nslots > ctx->compute_inflight && ctx->submit_seq >= ctx->compute_inflight) {
+		/* uploads run up to pipeline_depth batches ahead, but the kernels of at most STSGPU_COMPUTE_INFLIGHT (default 2; 0 = no
+		 * limit) batches interleave: a third batch of kernels only adds contention.  Measured end to end from host memory at depth 3:
+		 * no limit 9.07 ms per 1024 streams, 2: 8.91, 1: 10.3 */
+		Slot &prev = ctx->slots[(ctx->submit_seq - ctx->compute_inflight) % ctx->nslots];
 		CK(cudaStreamWaitEvent(sl, prev.ev_kdone, 0));
 	}
 	CK(cudaMemsetAsync(S.d_st, 0, (size_t) nstreams * lay.nst * sizeof(long long), sl));

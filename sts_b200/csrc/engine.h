@@ -58,6 +58,7 @@ struct stsgpu_ctx {
 	int device = 0, num_sms = 0;
 
 	int nslots = 2;
+	int compute_inflight = 2;	/* STSGPU_COMPUTE_INFLIGHT: > 0 = kernels of at most that many batches interleave (uploads still run ahead) */
 	bool overlap_batches = true;	/* false (STSGPU_SERIALIZE_BATCHES=1): kernels of consecutive batches do not interleave */
 	Slot slots[STS_MAX_SLOTS];
 	uint64_t submit_seq = 0;	/* the next submit / upload / generate uses slot submit_seq % nslots */
