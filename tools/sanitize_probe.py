@@ -50,3 +50,15 @@ eng.submit_ascii(text, 4, 0)
 eng.wait()
 print("ascii ok", eng.ascii_status())
 eng.close()
+
+# the device generators (k_gen.cu): ragged lengths, a stream far from the start, every template width of the strided
+# non-overlapping count (k_pattern.cu)
+for n in (1 << 20, 1000 * 8, 512 * 3 + 8):
+    eng = sts_b200.Engine(max_streams=3, n=n, test_mask=1 << 1)
+    for gen in (2, 4, 5):
+        eng.generate(gen, 7, 3)
+        eng.download_input(3)
+    eng.close()
+print("generators ok")
+for m in (8, 10, 12, 13, 15):
+    run("templates m=%d" % m, 2, n=(1 << 19) - 40, non_overlapping_m=m, test_mask=1 << 8)
