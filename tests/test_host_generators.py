@@ -75,3 +75,13 @@ def test_only_the_chained_generators_are_made_here(lib):
     for g in (0, 1, 2, 4, 5, 10):
         assert not lib.sts_gen_open(g, 1024)
     assert not lib.sts_gen_open(3, 1001)
+
+
+def test_random_lengths_and_counts_match_the_oracle(lib):
+    import random
+    rnd = random.Random(5)
+    for _ in range(25):
+        gen = rnd.choice([3, 6, 7, 8, 9])
+        n = 8 * rnd.randint(1, 300 if gen in (6, 7) else 3000)
+        k = rnd.randint(1, 4)
+        assert make(lib, gen, n, k) == G.generate(gen, n, k), (gen, n, k)
