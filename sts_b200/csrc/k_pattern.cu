@@ -18,6 +18,7 @@
  *
  * Algorithmic bytes: n/8 per stream per kernel (times the slice count for H > 15).
  */
+#include <stdlib.h>
 #include "common.cuh"
 
 #define PAT_THREADS 256		/* nonoverlapping: 2 KiB histograms, many CTAs per SM */
@@ -367,6 +368,117 @@ cyclic_hist16_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__
 	emit_levels(P, hist, red, H - 1, 0, 0u, s, st, apen_hist);
 }
 
+/*
+ * Serial at m = 16 with ApEn below 15 (the defaults): half the atomics.  ONE atomic counts the windows at TWO
+ * positions: the histogram is over the 17-bit windows at the EVEN positions, 2^17 8-bit counters in the same 128 KiB
+ * (a 17-bit window at p holds the 16-bit windows at p and p + 1; n is even, the stream cyclic).  Level 16 is needed
+ * only for its sum of squares, which is taken on the fly - count16[x] = W[2x] + W[2x+1] + W[x] + W[2^16 + x], four bins
+ * per thread and step from four word loads - and level 15 - count15[y] = the four bytes of word y + the two bytes of
+ * halfwords y and 2^15 + y - goes through registers (32 bins per thread) into 32-bit counters in the same memory,
+ * where the common level code takes over.  The byte counters hold 4 on average; as in the 16-bit kernel a wrapped
+ * field lowers the sum of all fields, so "sum == n / 2" proves the counts, and any other stream is flagged and redone by
+ * the sliced 32-bit kernel.
+ */
+__device__ __forceinline__ uint32_t bytesum4(uint32_t w)
+{
+	const uint32_t t = (w & 0x00FF00FFu) + ((w >> 8) & 0x00FF00FFu);
+	return (t & 0xFFFFu) + (t >> 16);
+}
+
+#ifndef HIST17_MAXREG
+#define HIST17_MAXREG 48
+#endif
+__global__ void __maxnreg__(HIST17_MAXREG)
+cyclic_hist17w_kernel(DevParams P, const uint32_t *__restrict__ in, long long *__restrict__ st,
+		      uint32_t *__restrict__ apen_hist, uint32_t *__restrict__ flags)
+{
+	extern __shared__ uint32_t hist[];			/* 2^15 words: first 2^17 byte counters, then 2^15 counters of level 15 */
+	__shared__ unsigned long long red[HIST_THREADS / 32];
+	__shared__ int ok_s;
+	const int64_t s = blockIdx.x;
+	const int words = 1 << 15;
+	for (int i = threadIdx.x; i < words; i += HIST_THREADS)
+		hist[i] = 0;
+	__syncthreads();
+	const uint32_t *__restrict__ w = in + s * P.pitch_words;
+	const int64_t n = P.n;
+	const int64_t groups = (n + 31) >> 5;
+	for (int64_t g = threadIdx.x; g < groups; g += HIST_THREADS) {
+		const int64_t j0 = g * 32;
+		uint32_t cur, nxt;
+		if (j0 + 64 <= n) {
+			cur = ldw(w, g);
+			nxt = ldw(w, g + 1);
+		} else {
+			cur = cyc32(w, j0, n);
+			nxt = cyc32(w, j0 + 32, n);
+		}
+		const int cnt = (n - j0 >= 32) ? 32 : (int) (n - j0);	/* even: n is a multiple of 8 */
+		if (cnt == 32) {
+#pragma unroll
+			for (int p = 0; p < 32; p += 2) {
+				const uint32_t v = __funnelshift_l(nxt, cur, p) >> 15;
+				atomicAdd(&hist[v >> 2], 1u << ((v & 3u) << 3));
+			}
+		} else {
+			for (int p = 0; p < cnt; p += 2) {
+				const uint32_t v = __funnelshift_l(nxt, cur, p) >> 15;
+				atomicAdd(&hist[v >> 2], 1u << ((v & 3u) << 3));
+			}
+		}
+	}
+	__syncthreads();
+	{
+		unsigned long long tot = 0;
+		for (int i = threadIdx.x; i < words; i += HIST_THREADS)
+			tot += bytesum4(hist[i]);
+		tot = block_sum_u64(tot, red);
+		if (threadIdx.x == 0) {
+			ok_s = (tot == (unsigned long long) (n >> 1)) ? 1 : 0;
+			flags[s] = ok_s ? 0u : 1u;
+		}
+		__syncthreads();
+		if (!ok_s)
+			return;
+	}
+	long long *o = st + s * P.nst;
+	{	/* level 16: only its sum of squares (serial.c:414-421 at m) */
+		unsigned long long sq = 0;
+		for (int q = threadIdx.x; q < (1 << 14); q += HIST_THREADS) {
+			const uint32_t h0 = hist[2 * q], h1 = hist[2 * q + 1];	/* W[2x], W[2x+1] for x = 4q .. 4q + 3 */
+			const uint32_t b0 = hist[q], b1 = hist[(1 << 14) + q];	/* W[x], W[2^16 + x] */
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const uint32_t hw = ((j < 2 ? h0 : h1) >> (16 * (j & 1))) & 0xFFFFu;
+				const unsigned long long c = (hw & 0xFFu) + (hw >> 8) + ((b0 >> (8 * j)) & 0xFFu) + ((b1 >> (8 * j)) & 0xFFu);
+				sq += c * c;
+			}
+		}
+		sq = block_sum_u64(sq, red);
+		if (threadIdx.x == 0)
+			atomicAdd((unsigned long long *) (o + P.st_off[STSGPU_TEST_SERIAL]), sq);
+	}
+	/* level 15 through registers: bins threadIdx.x + 1024 k, two 16-bit counts per register */
+	uint32_t c15[16];
+#pragma unroll
+	for (int k = 0; k < 32; k++) {
+		const int y = threadIdx.x + k * HIST_THREADS;
+		const uint32_t ha = (hist[y >> 1] >> (16 * (y & 1))) & 0xFFFFu;
+		const uint32_t hb = (hist[(1 << 14) + (y >> 1)] >> (16 * (y & 1))) & 0xFFFFu;
+		const uint32_t c = bytesum4(hist[y]) + (ha & 0xFFu) + (ha >> 8) + (hb & 0xFFu) + (hb >> 8);
+		if (k & 1)
+			c15[k >> 1] |= c << 16;
+		else
+			c15[k >> 1] = c;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < 32; k++)
+		hist[threadIdx.x + k * HIST_THREADS] = (k & 1) ? (c15[k >> 1] >> 16) : (c15[k >> 1] & 0xFFFFu);
+	__syncthreads();
+	emit_levels(P, hist, red, 15, 0, 0u, s, st, apen_hist);
+}
+
 cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_apen_hist, uint32_t *d_flags)
 {
 	if (!(P.enabled & ((1u << STSGPU_TEST_SERIAL) | (1u << STSGPU_TEST_APEN))))
@@ -381,8 +493,17 @@ cudaError_t launch_pattern(const DevParams &P, const LaunchCtx &L, uint32_t *d_a
 		e = cudaFuncSetAttribute(cyclic_hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 		if (e != cudaSuccess)
 			return e;
-		cyclic_hist16_kernel<<<(unsigned) L.nstreams, HIST_THREADS, (size_t) sizeof(uint32_t) << (P.hist_bits - 1), L.stream>>>(
-			P, L.d_in, L.d_st, d_apen_hist, d_flags);
+		const bool serial = (P.enabled & (1u << STSGPU_TEST_SERIAL)) != 0, apen = (P.enabled & (1u << STSGPU_TEST_APEN)) != 0;
+		static const bool wide_ok = !(getenv("STSGPU_HIST_WIDE") && atoi(getenv("STSGPU_HIST_WIDE")) == 0);
+		if (wide_ok && P.hist_bits == 16 && serial && P.serial_m == 16 && (!apen || P.apen_m + 1 < 16)) {
+			e = cudaFuncSetAttribute(cyclic_hist17w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+			if (e != cudaSuccess)
+				return e;
+			cyclic_hist17w_kernel<<<(unsigned) L.nstreams, HIST_THREADS, 128 * 1024, L.stream>>>(P, L.d_in, L.d_st, d_apen_hist, d_flags);
+		} else {
+			cyclic_hist16_kernel<<<(unsigned) L.nstreams, HIST_THREADS, (size_t) sizeof(uint32_t) << (P.hist_bits - 1), L.stream>>>(
+				P, L.d_in, L.d_st, d_apen_hist, d_flags);
+		}
 		only_flagged = d_flags;
 	}
 	dim3 grid((unsigned) L.nstreams, 1u << P.hist_slice_bits);
