@@ -16,6 +16,11 @@
  * on the host with the reference's own expression, including its `1 << M` quirk (:356-377).
  *
  * Algorithmic bytes: n/8 per stream.  Integer work: M steps x ~4.5 word-ops x ceil((M+1)/32) words.
+ *
+ * Tried in round 2 and measured slower (2.94 against 2.57 ms per 1024 streams): the per-step advance of C as one wide
+ * multiply-add per word (c_new * 2^31 + carry << 32, the multiplier a run-time value so that it stays an IMAD.WIDE on
+ * the FMA pipe) to take the shift off the ALU pipe that bounds the kernel; SASS confirmed SHF 2569 -> 0 and IMAD
+ * +5292 (the wide multiply and a move per word), but two FMA-pipe instructions cost more than the one SHF they replace.
  */
 #include <stdlib.h>
 #include "common.cuh"
