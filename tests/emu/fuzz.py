@@ -3,7 +3,8 @@
 tests/emu) against the oracle: random stream lengths (also not multiples of 32), random valid test parameters, random /
 biased / periodic / degenerate inputs; records compared like tests/test_gpu_parity.py::compare_with_oracle.
 
-usage: python tests/emu/fuzz.py [first_seed] [count]      (prints one line per case, exits 1 at the first mismatch)"""
+usage: python tests/emu/fuzz.py [first_seed] [count]      (prints one line per case, exits 1 at the first mismatch)
+STS_FUZZ_GPU=1 runs the same cases through the real engine (sts_b200/libstsgpu.so) on cuda:0 instead of the emulator."""
 import os
 import sys
 
@@ -88,7 +89,10 @@ def one_case(sts, seed):
 def main():
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    sts = emu_binding()
+    if os.environ.get("STS_FUZZ_GPU", "") not in ("", "0"):	# the same cases through the product on a B200
+        import sts_b200 as sts
+    else:
+        sts = emu_binding()
     for seed in range(first, first + count):
         try:
             print("seed %d ok: %s" % (seed, one_case(sts, seed)), flush=True)
