@@ -9,10 +9,11 @@ sys.path.insert(0, ROOT)
 import sts_b200  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 eng = sts_b200.Engine(max_streams=B, n=10 ** 7, linear_complexity_M=5000, non_overlapping_m=10, apen_m=16, serial_m=16)
 eng.generate_lcg(0, B)
 eng.set_profiling(1)
-for r in range(3):
+for r in range(REPS):
     eng.submit_resident(B, 0)
     eng.wait()
 tot = eng.last_batch_ms()
