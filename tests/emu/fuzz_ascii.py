@@ -15,7 +15,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from emu_util import emu_binding  # noqa: E402
 from golden_util import ascii_seek_rule_streams  # noqa: E402
 
-sts = emu_binding()
+if os.environ.get("STS_FUZZ_GPU", "") not in ("", "0"):	# the same cases through the product on a B200
+    import sts_b200 as sts
+else:
+    sts = emu_binding()
 bad = 0
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     rng = np.random.RandomState(seed)

@@ -10,7 +10,10 @@ import numpy as np
 from emu_util import emu_binding
 from oracle import oracle as O
 from golden_util import rel_err
-sts = emu_binding()
+if os.environ.get("STS_FUZZ_GPU", "") not in ("", "0"):	# the same cases through the product on a B200
+    import sts_b200 as sts
+else:
+    sts = emu_binding()
 NONP = -99999999.0
 bad = 0
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):

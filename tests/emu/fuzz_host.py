@@ -20,7 +20,10 @@ from emu_util import emu_host_driver  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "sts")
-EXE = emu_host_driver()
+if os.environ.get("STS_FUZZ_GPU", "") not in ("", "0"):	# the product's own host driver on a B200
+    EXE = os.path.join(ROOT, "sts_b200", "host", "stsb200")
+else:
+    EXE = emu_host_driver()
 
 
 def body(path):
