@@ -12,9 +12,9 @@ def shard_range(total_iterations, rank, nranks):
     return rank * per, (rank + 1) * per
 
 
-def run_sharded(eng, total, rank, world, batch, collect=True, first_stream=0, inflight=None, timer=None):
-    """BASELINE config 3: `total` LCG streams (tools/generators 1, made on the device by skip-ahead from
-    `first_stream`), rank r testing the `-j r` slice in batches of `batch` streams with the engine in gather mode
+def run_sharded(eng, total, rank, world, batch, collect=True, first_stream=0, inflight=None, timer=None, generator=1):
+    """BASELINE config 3: `total` streams of tools/generators `generator` (1 = LCG, the default; 2, 4, 5 also jump ahead:
+    stsgpu_generate), made on the device by skip-ahead from `first_stream`, rank r testing the `-j r` slice in batches of `batch` streams with the engine in gather mode
     (stsgpu_gather_begin: every batch ends with the exchange of its p-values to rank 0 over NCCL).
 
     Returns, on rank 0 with collect=True, the p-values of all world * (total // world) streams in iteration (= job)
@@ -43,7 +43,7 @@ def run_sharded(eng, total, rank, world, batch, collect=True, first_stream=0, in
         timer()
     pending = 0
     for b in range(nb):
-        eng.generate_lcg(first_stream + lo + b * batch, batch)
+        eng.generate(generator, first_stream + lo + b * batch, batch)
         eng.submit_resident(batch, lo + b * batch)
         pending += 1
         if pending == depth:

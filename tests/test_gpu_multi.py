@@ -51,6 +51,17 @@ def test_ragged_sharding_and_small_batches():
     assert out["ok"] and out["total_streams"] == 576, out
 
 
+def test_sharding_of_a_jump_ahead_generator():
+    """the same with generator 2 of tools/generators (512-bit quadratic congruential, stsgpu_generate): every rank jumps to
+    its own slice of the one sequence; gathered array against one GPU making all streams, and the oracle"""
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    out = run_ranks(2, [os.path.join(ROOT, "tools", "config3_check.py"), "--total", "256", "--batch", "64", "--oracle-streams", "6",
+                        "--generator", "2"])
+    assert out["ok"] and out["generator"] == 2 and out["gathered_identical_to_single_gpu"], out
+
+
 def test_bench_reports_gather_check_and_strong_scaling():
     """bench.py --gpus N: the gathered p-values of the last timed step are verified on rank 0 (gather_check.ok) and the
     config-3 strong-scaling block is present"""

@@ -29,6 +29,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--total", type=int, default=16384)
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--oracle-streams", type=int, default=16)
+ap.add_argument("--generator", type=int, default=1, help="tools/generators number made on the device: 1, 2, 4 or 5")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -43,7 +44,8 @@ eng.comm_init(uid[0], rank, world)
 marks = []
 torch.cuda.synchronize()
 dist.barrier()
-allpv = run_sharded(eng, args.total, rank, world, B, collect=True, timer=lambda: marks.append(time.perf_counter()))
+allpv = run_sharded(eng, args.total, rank, world, B, collect=True, timer=lambda: marks.append(time.perf_counter()),
+                    generator=args.generator)
 dist.barrier()
 sec = torch.tensor([marks[1] - marks[0]], dtype=torch.float64, device="cuda")
 dist.all_reduce(sec, op=dist.ReduceOp.MAX)
@@ -58,7 +60,7 @@ if rank == 0:
     single = np.empty_like(allpv)
     with sts_b200.Engine(device=local, max_streams=B, pipeline_depth=2) as one:
         for b in range(world * per // B):
-            one.generate_lcg(b * B, B)
+            one.generate(args.generator, b * B, B)
             one.submit_resident(B, b * B)
             one.wait()
             single[b * B:(b + 1) * B] = one.results(copy=False)[0]
@@ -71,7 +73,7 @@ if rank == 0:
                      set(shard_range(args.total, r, world)[1] - 1 for r in range(world)))
         raws = []
         for i in idx:
-            one.generate_lcg(i, 1)
+            one.generate(args.generator, i, 1)
             raws.append(one.download_input(1))
         raw = np.concatenate(raws)
     bad_rows = np.flatnonzero((allpv != single).any(axis=1))
@@ -87,7 +89,7 @@ if rank == 0:
     rel[:, c3][np.abs(got[:, c3] - opv[:, c3]) <= 1e-13] = 0.0
     worst = float(rel.max())
     ok = identical and worst <= 1e-9
-    print(json.dumps({"config": "BASELINE config 3", "ranks": world, "total_streams": world * per, "batch": B,
+    print(json.dumps({"config": "BASELINE config 3", "generator": args.generator, "ranks": world, "total_streams": world * per, "batch": B,
                       "seconds_sharded": float(sec.item()), "gbit_per_s": world * per * n / float(sec.item()) / 1e9,
                       "gathered_identical_to_single_gpu": bool(identical), "first_bad_rows": bad_rows[:8].tolist(),
                       "oracle_streams": idx, "oracle_max_rel_err": worst, "ok": bool(ok)}))
