@@ -365,6 +365,8 @@ def test_assessment_tallies_match_reference_report(sts, oracle):
     (11, dict(n=1 << 18, apen_m=1)),                     # ApEn: H = 2
     (11, dict(n=1 << 20, apen_m=14)),                    # ApEn: H = 15
     (14, dict(n=1 << 21, serial_m=18)),                  # Serial: sliced 32-bit histogram, 8 slices
+    (14, dict(n=(1 << 20) + 40, serial_m=16)),           # Serial: the 17-bit-window kernel with a partial last group (n % 32 = 8)
+    (14, dict(n=1 << 20, serial_m=15)),                  # Serial: H = 15, the 16-bit-counter kernel
     (8, dict(n=1 << 18, non_overlapping_m=8)),
     (8, dict(n=1 << 18, non_overlapping_m=12)),              # wide-window stride 2
     (8, dict(n=(1 << 18) + 8 * 13, non_overlapping_m=10)),   # stride 4 with a partial last group of window starts
