@@ -538,7 +538,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu_per_step": B, "bits_per_stream": N_BITS,
                        "l2": "input per step (128 MiB) exceeds L2; the FFT intermediate (8 GiB per step) flushes it",
-                       "pipeline": "%d batch slots per GPU: 2 in flight for resident input, %d for host input (the upload of one overlaps the kernels of the others)" % (DEPTH, DEPTH),
+                       "pipeline": "%d batch slots per GPU: 2 in flight for resident input, %d for host input (uploads run that far ahead, the kernels of at most two batches interleave)" % (DEPTH, DEPTH),
                        "sharding": "rank r tests streams [r*B,(r+1)*B), p-values gathered to rank 0 over NCCL in gather mode "
                                    "(the exchange of a batch is queued behind its kernels and overlaps the next batches)"},
             "device_ms_per_step": dev_step_ms,
